@@ -1,0 +1,324 @@
+"""bench.py — env-steps/s of the gym_ffmp hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE.json configs[2] per-GPU shape — 4096 envs/GPU x 128x128 grids,
+W=100 local maps, goal re-sampled every reset (flow-field recompute per reset), uniform random actions.
+One "step" = one batched env step of every env on every GPU.  Weak scaling: envs shard by global id with
+no data-path collective (SPEC.md §3); the only collective is the max-over-ranks of the timing.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec (flow-field+dynamics)"
+UNIT = "env-steps/s"
+HBM_FALLBACK_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--warmup", type=int, default=500)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--grid", type=int, default=128)
+    ap.add_argument("--window", type=int, default=100)
+    ap.add_argument("--ring", type=int, default=8)
+    ap.add_argument("--slots", type=int, default=3)
+    ap.add_argument("--goal-mode", type=int, default=0)
+    ap.add_argument("--p-occ", type=float, default=0.10)
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--chunk", type=int, default=250, help="steps per ffmp_rollout call (action block is reused)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the flow-field / e2e / roofline side measurements")
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {"workload": f"BASELINE configs[2] per-GPU shape: {a.envs} envs/GPU x {a.grid}x{a.grid} grid, W={a.window}, "
+                        f"goal {'re-sampled each reset' if a.goal_mode == 0 else 'static'}, uniform random actions",
+            "envs_per_gpu": a.envs, "grid": a.grid, "window": a.window, "ring": a.ring, "slots": a.slots,
+            "p_occ": a.p_occ, "block_shift": 3, "max_steps": 200, "global_envs": a.envs * n_gpus,
+            "parallelism": f"env-sharded x{n_gpus}, no data-path collective",
+            "l2": "no explicit flush: resident inputs (flow planes + frame ring) exceed the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampling (recipe: B200_PROFILING.md)
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix="ffmp_clocks_", suffix=".csv")
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); smax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU legs: the oracle port on the host cores (test infrastructure used as the *baseline*, never shipped)
+# ------------------------------------------------------------------------------------------------------
+def cpu_port_throughput(a, envs_per_thread, steps, warmup, threads):
+    """env-steps/s of the C oracle (oracle/ffmp_oracle.c) with `threads` host threads, each stepping its own
+    shard of `envs_per_thread` envs of the bench workload (ctypes releases the GIL)."""
+    import numpy as np
+    import oracle
+    shards = [oracle.OracleVectorEnv(envs_per_thread, grid=a.grid, window=a.window, goal_mode=a.goal_mode,
+                                     p_occ=a.p_occ, seed=a.seed, env_id_base=i * envs_per_thread) for i in range(threads)]
+    rng = np.random.default_rng(a.seed)
+    acts = rng.integers(0, 28, (warmup + steps, threads, envs_per_thread))
+    for s in shards:
+        s.reset()
+
+    def run(lo, hi):
+        def work(i):
+            for t in range(lo, hi):
+                shards[i].step(acts[t, i])
+        th = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+        t0 = time.perf_counter()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return time.perf_counter() - t0
+
+    run(0, warmup)
+    dt = run(warmup, warmup + steps)
+    for s in shards:
+        s.close()
+    return threads * envs_per_thread * steps / dt, dt
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is Python with the path's
+    flow field / physics / scenario generation living in un-vendored ROS nodes, so nothing compiles
+    into oracle/_ref; the timed code is the oracle port (kind "port") on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    envs_per_thread = 32
+    steps = max(1, min(a.steps, 200))
+    warmup = max(3, min(a.warmup, 10))
+    v, dt = cpu_port_throughput(a, envs_per_thread, steps, warmup, cores)
+    sample = f"{cores} threads x {envs_per_thread} envs x {steps} steps of the same workload (C oracle port, gcc -O2)"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic", "config": workload_config(a, a.gpus),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    import flow_field_based_motion_planner_b200 as ffmp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    N = a.envs
+
+    env = ffmp.FFMPVectorEnv(N, grid=a.grid, window=a.window, ring=a.ring, slots=a.slots, goal_mode=a.goal_mode,
+                             p_occ=a.p_occ, seed=a.seed, env_id_base=rank * N, device=f"cuda:{local}")
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(a.seed + rank)
+    chunk = max(1, min(a.chunk, a.steps))
+    actions = torch.randint(0, 28, (chunk, N), generator=gen, device=dev, dtype=torch.int64)
+    env.reset()
+    torch.cuda.synchronize()
+
+    def run_steps(k):
+        done_steps = 0
+        while done_steps < k:
+            t = min(chunk, k - done_steps)
+            env.rollout(actions[:t])
+            done_steps += t
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- headline: K device-resident steps, CUDA events, max over ranks --------------------------
+    run_steps(max(3, a.warmup))
+    env.join()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    run_steps(a.steps)
+    env.join()                    # the timed region ends only when every queued regeneration has finished
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * N * a.steps / (ms * 1e-3)
+
+    extras = {}
+    e2e = None
+    roofline = None
+    if not a.no_extras:
+        # ---- e2e: public Python API with HOST buffers (pinned actions in, reward/done/goal/velocity out) ----
+        k2 = max(10, min(a.steps, 2000))
+        host_actions = [torch.randint(0, 28, (N,), dtype=torch.int64).pin_memory() for _ in range(16)]
+        for i in range(20):
+            env.step_host(host_actions[i % 16])
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(k2):
+            env.step_host(host_actions[i % 16])
+        env.join()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * N * k2 / dt, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step * world,
+               "d2h_bytes_per_step": env.d2h_bytes_per_step * world, "steps": k2,
+               "note": "FFMPVectorEnv.step_host: pinned int64 actions H2D, reward/done/flags/relative_goal/velocity D2H "
+                       "and a stream sync every step; local_map observations stay on the device for the learner"}
+
+        # ---- roofline of the dominant kernel (step_kernel), timed live with CUDA events on its stream ----
+        if rank == 0:
+            peaks = {}
+            try:
+                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except (OSError, ValueError):
+                pass
+            peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
+            reps = 200
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            env.join()
+            torch.cuda.synchronize()
+            for i in range(reps):
+                evs[i][0].record()
+                env.step(actions[i % chunk])
+                evs[i][1].record()
+            torch.cuda.synchronize()
+            times = sorted(x.elapsed_time(y) for x, y in evs)
+            avg_ms = sum(times) / len(times)
+            bytes_per_launch = N * (2 * a.window * a.window + 146)
+            achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+            roofline = {"kernel": "step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": None,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback",
+                        "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
+                        "median_launch_ms": times[len(times) // 2]}
+
+            # ---- flow-field operator: grid cells/s and fraction of the 6 B/cell roofline ----
+            gids = torch.arange(N, device=dev)
+            occ, scen = ffmp.ops.generate_scenarios(gids, torch.zeros_like(gids), a.grid, p_occ=a.p_occ, seed=a.seed)
+            goals = scen[:, 5:7].contiguous()
+            for _ in range(3):
+                ffmp.ops.flow_field(occ, goals)
+            torch.cuda.synchronize()
+            ff = []
+            for _ in range(5):
+                x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                x.record()
+                ffmp.ops.flow_field(occ, goals)
+                y.record()
+                torch.cuda.synchronize()
+                ff.append(x.elapsed_time(y))
+            ff_ms = sum(ff) / len(ff)
+            cells = N * a.grid * a.grid
+            extras["flow_field"] = {"cells_per_s": cells / (ff_ms * 1e-3), "ms": ff_ms, "batch": N, "grid": a.grid,
+                                    "algorithmic_bytes_per_cell": 6,
+                                    "achieved_gbs": cells * 6 / (ff_ms * 1e-3) / 1e9,
+                                    "frac_of_hbm_peak": cells * 6 / (ff_ms * 1e-3) / 1e9 / peak}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        v, dt = cpu_port_throughput(a, 64, 300, 10, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"64 envs x 300 steps of the same workload, single thread, {dt:.1f} s (C oracle port)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32+u8", "data": "synthetic", "config": workload_config(a, world), "clocks": clocks,
+                "e2e": e2e, "gpu_launches": 3 * a.steps, "roofline": roofline, "cpu_baseline": cpu}
+        line.update(extras)
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

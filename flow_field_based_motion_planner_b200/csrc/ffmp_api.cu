@@ -1,0 +1,446 @@
+// ffmp_api.cu — the C-ABI of libffmp_b200.so (include/ffmp_b200.h): handle, buffer binding, stream /
+// event plumbing for the background scenario regeneration, and the stateless operators.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/ffmp_b200.h"
+#include "ffmp_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *what, cudaError_t ce = cudaSuccess) {
+    g_err = what;
+    if (ce != cudaSuccess) {
+        g_err += ": ";
+        g_err += cudaGetErrorString(ce);
+    }
+    return code;
+}
+
+#define CK(call)                                                  \
+    do {                                                          \
+        cudaError_t ce_ = (call);                                 \
+        if (ce_ != cudaSuccess) return fail(FFMP_ERR_CUDA, #call, ce_); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
+constexpr int MAX_LISTS = 7;
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int check_device(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(FFMP_ERR_DEVICE, "no CUDA device available (there is no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return fail(FFMP_ERR_DEVICE, "device ordinal out of range");
+    cudaDeviceProp prop;
+    cudaError_t ce = cudaGetDeviceProperties(&prop, device);
+    if (ce != cudaSuccess) return fail(FFMP_ERR_CUDA, "cudaGetDeviceProperties", ce);
+    if (prop.major != 10 || prop.minor != 0)
+        return fail(FFMP_ERR_DEVICE, "device is not sm_100 (B200); this library carries sm_100a code only");
+    return FFMP_OK;
+}
+
+int check_cfg(const ffmp_cfg *c) {
+    if (!c) return fail(FFMP_ERR_ARG, "cfg is null");
+    if (c->abi_version != FFMP_ABI_VERSION) return fail(FFMP_ERR_ABI, "cfg.abi_version != FFMP_ABI_VERSION");
+    if (c->num_envs <= 0) return fail(FFMP_ERR_ARG, "num_envs must be > 0");
+    if (c->grid < 16 || c->grid > 1024 || (c->grid % 4)) return fail(FFMP_ERR_ARG, "grid must be a multiple of 4 in [16,1024]");
+    if (!ffmp::flow_field_supported(c->grid)) return fail(FFMP_ERR_ARG, "grid > 128 is not supported by this build");
+    if (c->window < 4 || c->window > 256 || (c->window % 4)) return fail(FFMP_ERR_ARG, "window must be a multiple of 4 in [4,256]");
+    if (c->ring < 2 || c->ring > 1024) return fail(FFMP_ERR_ARG, "ring must be in [2,1024]");
+    if (c->slots < 2 || c->slots > MAX_LISTS + 1) return fail(FFMP_ERR_ARG, "slots must be in [2,8]");
+    if (c->max_steps <= 0) return fail(FFMP_ERR_ARG, "max_steps must be > 0");
+    if (c->goal_mode != 0 && c->goal_mode != 1) return fail(FFMP_ERR_ARG, "goal_mode must be 0 or 1");
+    if (c->block_shift < 0 || c->block_shift > 8) return fail(FFMP_ERR_ARG, "block_shift must be in [0,8]");
+    if (!(c->dt > 0.0f)) return fail(FFMP_ERR_ARG, "dt must be > 0");
+    return FFMP_OK;
+}
+
+struct Workspace {
+    size_t error_word, lists, actions, hi, total;
+    size_t list_stride;  // bytes per regen list block: [count,ticket,pad..64B][env u32 N][episode u32 N]
+};
+
+Workspace workspace_layout(const ffmp_cfg *c) {
+    Workspace w{};
+    const size_t N = static_cast<size_t>(c->num_envs);
+    size_t off = 0;
+    w.error_word = off; off += 256;
+    w.list_stride = align_up(256 + 2 * N * sizeof(uint32_t), 256);
+    w.lists = off; off += w.list_stride * static_cast<size_t>(c->slots - 1);
+    w.actions = off; off += align_up(N * sizeof(int64_t), 256);
+    w.hi = off;
+    off += align_up(static_cast<size_t>(ffmp::flow_field_max_grid(c->grid)) * ffmp::flow_field_scratch_words(c->grid) * 4, 256);
+    w.total = off;
+    return w;
+}
+
+}  // namespace
+
+struct ffmp_handle {
+    ffmp_cfg cfg;
+    ffmp_buffers b;
+    Workspace ws;
+    bool bound = false, ready = false;
+    cudaStream_t side = nullptr;
+    int nlist = 1;
+    cudaEvent_t ev_step[MAX_LISTS], ev_regen[MAX_LISTS];
+    bool regen_pending[MAX_LISTS];
+    uint64_t step_index = 0;
+    int p = 1;  // newest ring slot
+    int ff_grid = 0, sc_grid = 0;
+
+    uint32_t *error_word() const { return reinterpret_cast<uint32_t *>(static_cast<char *>(b.workspace) + ws.error_word); }
+    char *list_base(int l) const { return static_cast<char *>(b.workspace) + ws.lists + ws.list_stride * l; }
+    uint32_t *list_count(int l) const { return reinterpret_cast<uint32_t *>(list_base(l)); }
+    uint32_t *list_ticket(int l) const { return reinterpret_cast<uint32_t *>(list_base(l)) + 1; }
+    uint32_t *list_env(int l) const { return reinterpret_cast<uint32_t *>(list_base(l) + 256); }
+    uint32_t *list_episode(int l) const { return list_env(l) + cfg.num_envs; }
+    int64_t *actions() const { return reinterpret_cast<int64_t *>(static_cast<char *>(b.workspace) + ws.actions); }
+    uint32_t *hi_scratch() const { return reinterpret_cast<uint32_t *>(static_cast<char *>(b.workspace) + ws.hi); }
+};
+
+namespace {
+
+ffmp::ScenarioArgs scenario_args(const ffmp_handle *h) {
+    ffmp::ScenarioArgs a{};
+    const ffmp_cfg &c = h->cfg;
+    a.G = c.grid; a.goal_mode = c.goal_mode; a.block_shift = c.block_shift; a.slot_mode = 1; a.S = c.slots; a.N = c.num_envs;
+    a.p_thresh = c.p_thresh; a.env_id_base = c.env_id_base; a.seed = c.seed;
+    a.occ = h->b.occ; a.scen = h->b.scen;
+    return a;
+}
+
+ffmp::FlowArgs flow_args(const ffmp_handle *h) {
+    ffmp::FlowArgs a{};
+    const ffmp_cfg &c = h->cfg;
+    a.G = c.grid; a.slot_mode = 1; a.S = c.slots; a.N = c.num_envs;
+    a.occ = h->b.occ; a.scen = h->b.scen; a.cost = h->b.cost; a.flow = h->b.flow;
+    a.hi_scratch = h->hi_scratch();
+    return a;
+}
+
+ffmp::StepArgs step_args(const ffmp_handle *h) {
+    ffmp::StepArgs a{};
+    const ffmp_cfg &c = h->cfg;
+    const ffmp_buffers &b = h->b;
+    a.N = c.num_envs; a.G = c.grid; a.W = c.window; a.K = c.ring; a.S = c.slots; a.max_steps = c.max_steps; a.dt = c.dt;
+    a.flow = b.flow; a.scen = b.scen; a.state = b.state; a.frames = b.frames;
+    a.rel_goal = b.rel_goal; a.velocity = b.velocity; a.reward = b.reward;
+    a.term_rel_goal = b.term_rel_goal; a.term_velocity = b.term_velocity; a.fin_return = b.fin_return;
+    a.done = b.done; a.flags = b.flags; a.fin_length = b.fin_length;
+    a.error_word = h->error_word();
+    return a;
+}
+
+// One env-step-like call (mode 0 step, mode 1 masked reset) with the background regeneration queued.
+int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *mask, cudaStream_t st) {
+    const int l = static_cast<int>(h->step_index % static_cast<uint64_t>(h->nlist));
+    if (h->regen_pending[l]) {
+        // the regeneration that last used list `l` (S-1 ticks ago) must be complete: it re-armed the
+        // list and filled the scenario slot an env may switch to in this tick
+        CK(cudaStreamWaitEvent(st, h->ev_regen[l], 0));
+        h->regen_pending[l] = false;
+    }
+    ffmp::StepArgs a = step_args(h);
+    a.mode = mode; a.actions = actions; a.mask = mask;
+    if (mode == 0) {
+        if (h->cfg.ring == 2) { a.slot_new = 1; a.write_older = 1; }
+        else if (h->p + 1 < h->cfg.ring) { h->p += 1; a.slot_new = h->p; a.write_older = 0; }
+        else { h->p = 1; a.slot_new = 1; a.write_older = 1; }
+    } else {
+        a.slot_new = h->p; a.write_older = 0;
+    }
+    a.regen_env = h->list_env(l); a.regen_episode = h->list_episode(l); a.regen_count = h->list_count(l);
+    CK(ffmp::launch_step(a, st));
+    CK(cudaEventRecord(h->ev_step[l], st));
+    CK(cudaStreamWaitEvent(h->side, h->ev_step[l], 0));
+    ffmp::ScenarioArgs sa = scenario_args(h);
+    sa.env_idx = h->list_env(l); sa.episode = h->list_episode(l); sa.count_ptr = h->list_count(l);
+    CK(ffmp::launch_scenarios(sa, h->sc_grid, h->side));
+    ffmp::FlowArgs fa = flow_args(h);
+    fa.env_idx = h->list_env(l); fa.episode = h->list_episode(l); fa.count_ptr = h->list_count(l);
+    fa.ticket = h->list_ticket(l); fa.count_reset = h->list_count(l);
+    CK(ffmp::launch_flow_field(fa, h->ff_grid, h->side));
+    CK(cudaEventRecord(h->ev_regen[l], h->side));
+    h->regen_pending[l] = true;
+    h->step_index += 1;
+    return FFMP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *ffmp_last_error(void) { return g_err.c_str(); }
+uint32_t ffmp_abi_version(void) { return FFMP_ABI_VERSION; }
+
+int ffmp_query_sizes(const ffmp_cfg *cfg, ffmp_sizes *out) {
+    if (int rc = check_cfg(cfg)) return rc;
+    if (!out) return fail(FFMP_ERR_ARG, "out is null");
+    const size_t N = cfg->num_envs, G = cfg->grid, W = cfg->window, K = cfg->ring, S = cfg->slots;
+    out->occ = S * N * G * G;
+    out->cost = S * N * G * G * sizeof(int32_t);
+    out->flow = S * N * G * G;
+    out->scen = S * N * ffmp::SC_WORDS * sizeof(uint32_t);
+    out->state = N * ffmp::ST_WORDS * sizeof(uint32_t);
+    out->frames = N * K * W * W;
+    out->vec2 = N * 2 * sizeof(float);
+    out->vec1 = N * sizeof(float);
+    out->bytes1 = N;
+    out->workspace = workspace_layout(cfg).total;
+    return FFMP_OK;
+}
+
+int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
+    if (!out) return fail(FFMP_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (int rc = check_cfg(cfg)) return rc;
+    if (int rc = check_device(cfg->device)) return rc;
+    DeviceGuard guard(cfg->device);
+    ffmp_handle *h = new (std::nothrow) ffmp_handle();
+    if (!h) return fail(FFMP_ERR_ARG, "out of host memory");
+    h->cfg = *cfg;
+    h->ws = workspace_layout(cfg);
+    h->nlist = cfg->slots - 1;
+    std::memset(&h->b, 0, sizeof(h->b));
+    for (int i = 0; i < MAX_LISTS; ++i) { h->ev_step[i] = nullptr; h->ev_regen[i] = nullptr; h->regen_pending[i] = false; }
+    cudaError_t ce = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+    for (int i = 0; i < h->nlist && ce == cudaSuccess; ++i) {
+        ce = cudaEventCreateWithFlags(&h->ev_step[i], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_regen[i], cudaEventDisableTiming);
+    }
+    if (ce != cudaSuccess) {
+        ffmp_destroy(h);
+        return fail(FFMP_ERR_CUDA, "stream/event creation", ce);
+    }
+    const int maxg = ffmp::flow_field_max_grid(cfg->grid);
+    h->ff_grid = cfg->num_envs < maxg ? cfg->num_envs : maxg;
+    h->sc_grid = cfg->num_envs < 148 * 8 ? cfg->num_envs : 148 * 8;
+    *out = h;
+    return FFMP_OK;
+}
+
+int ffmp_bind(ffmp_handle *h, const ffmp_buffers *bufs) {
+    if (!h || !bufs) return fail(FFMP_ERR_ARG, "null argument");
+    const void *ptrs[] = {bufs->occ, bufs->cost, bufs->flow, bufs->scen, bufs->state, bufs->frames, bufs->rel_goal,
+                          bufs->velocity, bufs->reward, bufs->done, bufs->flags, bufs->term_rel_goal, bufs->term_velocity,
+                          bufs->fin_return, bufs->fin_length, bufs->workspace};
+    for (const void *p : ptrs)
+        if (!p) return fail(FFMP_ERR_ARG, "every ffmp_buffers pointer must be set");
+    const uintptr_t aligned[] = {reinterpret_cast<uintptr_t>(bufs->occ), reinterpret_cast<uintptr_t>(bufs->cost),
+                                 reinterpret_cast<uintptr_t>(bufs->flow), reinterpret_cast<uintptr_t>(bufs->frames),
+                                 reinterpret_cast<uintptr_t>(bufs->state), reinterpret_cast<uintptr_t>(bufs->scen),
+                                 reinterpret_cast<uintptr_t>(bufs->workspace)};
+    for (uintptr_t p : aligned)
+        if (p % 16) return fail(FFMP_ERR_ARG, "plane / frame / state / workspace buffers must be 16-byte aligned");
+    h->b = *bufs;
+    h->bound = true;
+    h->ready = false;
+    return FFMP_OK;
+}
+
+int ffmp_destroy(ffmp_handle *h) {
+    if (!h) return FFMP_OK;
+    DeviceGuard guard(h->cfg.device);
+    if (h->side) {
+        cudaStreamSynchronize(h->side);
+        cudaStreamDestroy(h->side);
+    }
+    for (int i = 0; i < MAX_LISTS; ++i) {
+        if (h->ev_step[i]) cudaEventDestroy(h->ev_step[i]);
+        if (h->ev_regen[i]) cudaEventDestroy(h->ev_regen[i]);
+    }
+    delete h;
+    return FFMP_OK;
+}
+
+int ffmp_reset(ffmp_handle *h, const uint8_t *mask_dev, void *stream) {
+    if (!h) return fail(FFMP_ERR_ARG, "handle is null");
+    if (!h->bound) return fail(FFMP_ERR_STATE, "ffmp_bind must be called before ffmp_reset");
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (mask_dev) {
+        if (!h->ready) return fail(FFMP_ERR_STATE, "a full ffmp_reset must precede a masked reset");
+        return run_tick(h, 1, nullptr, mask_dev, st);
+    }
+    // full reset: drain the background stream, regenerate every scenario slot, begin episode 0 everywhere
+    for (int l = 0; l < h->nlist; ++l)
+        if (h->regen_pending[l]) { CK(cudaStreamWaitEvent(st, h->ev_regen[l], 0)); h->regen_pending[l] = false; }
+    const ffmp_cfg &c = h->cfg;
+    CK(cudaMemsetAsync(h->b.state, 0, static_cast<size_t>(c.num_envs) * ffmp::ST_WORDS * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(h->b.workspace, 0, h->ws.actions, st));  // error word + regen lists
+    for (int s = 0; s < c.slots; ++s) {
+        ffmp::ScenarioArgs sa = scenario_args(h);
+        sa.count = c.num_envs; sa.episode_const = static_cast<uint32_t>(s);
+        CK(ffmp::launch_scenarios(sa, h->sc_grid, st));
+        ffmp::FlowArgs fa = flow_args(h);
+        fa.count = c.num_envs; fa.episode_const = static_cast<uint32_t>(s);
+        CK(ffmp::launch_flow_field(fa, h->ff_grid, st));
+    }
+    h->p = 1;
+    h->step_index = 0;
+    ffmp::StepArgs a = step_args(h);
+    a.mode = 2; a.slot_new = 1; a.write_older = 1;
+    a.regen_env = h->list_env(0); a.regen_episode = h->list_episode(0); a.regen_count = h->list_count(0);
+    CK(ffmp::launch_step(a, st));
+    h->ready = true;
+    return FFMP_OK;
+}
+
+int ffmp_step(ffmp_handle *h, const int64_t *actions_dev, void *stream) {
+    if (!h || !actions_dev) return fail(FFMP_ERR_ARG, "null argument");
+    if (!h->ready) return fail(FFMP_ERR_STATE, "ffmp_reset must be called before ffmp_step");
+    DeviceGuard guard(h->cfg.device);
+    return run_tick(h, 0, actions_dev, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int ffmp_rollout(ffmp_handle *h, const int64_t *actions_dev, int32_t T, void *stream) {
+    if (!h || !actions_dev || T < 0) return fail(FFMP_ERR_ARG, "bad argument");
+    if (!h->ready) return fail(FFMP_ERR_STATE, "ffmp_reset must be called before ffmp_rollout");
+    DeviceGuard guard(h->cfg.device);
+    for (int32_t t = 0; t < T; ++t)
+        if (int rc = run_tick(h, 0, actions_dev + static_cast<size_t>(t) * h->cfg.num_envs, nullptr,
+                              static_cast<cudaStream_t>(stream)))
+            return rc;
+    return FFMP_OK;
+}
+
+int ffmp_step_host(ffmp_handle *h, const int64_t *actions_host, float *reward_host, uint8_t *done_host,
+                   uint8_t *flags_host, float *rel_goal_host, float *velocity_host, void *stream) {
+    if (!h || !actions_host) return fail(FFMP_ERR_ARG, "null argument");
+    if (!h->ready) return fail(FFMP_ERR_STATE, "ffmp_reset must be called before ffmp_step_host");
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t N = h->cfg.num_envs;
+    CK(cudaMemcpyAsync(h->actions(), actions_host, N * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    if (int rc = run_tick(h, 0, h->actions(), nullptr, st)) return rc;
+    if (reward_host) CK(cudaMemcpyAsync(reward_host, h->b.reward, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (done_host) CK(cudaMemcpyAsync(done_host, h->b.done, N, cudaMemcpyDeviceToHost, st));
+    if (flags_host) CK(cudaMemcpyAsync(flags_host, h->b.flags, N, cudaMemcpyDeviceToHost, st));
+    if (rel_goal_host) CK(cudaMemcpyAsync(rel_goal_host, h->b.rel_goal, N * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (velocity_host) CK(cudaMemcpyAsync(velocity_host, h->b.velocity, N * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return FFMP_OK;
+}
+
+int ffmp_obs_slot(const ffmp_handle *h, int32_t *newest_slot) {
+    if (!h || !newest_slot) return fail(FFMP_ERR_ARG, "null argument");
+    *newest_slot = h->p;
+    return FFMP_OK;
+}
+
+int ffmp_join(ffmp_handle *h, void *stream) {
+    if (!h) return fail(FFMP_ERR_ARG, "handle is null");
+    DeviceGuard guard(h->cfg.device);
+    for (int l = 0; l < h->nlist; ++l)
+        if (h->regen_pending[l]) CK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), h->ev_regen[l], 0));
+    return FFMP_OK;
+}
+
+int ffmp_error_word(ffmp_handle *h, uint32_t *out, void *stream) {
+    if (!h || !out) return fail(FFMP_ERR_ARG, "null argument");
+    if (!h->bound) return fail(FFMP_ERR_STATE, "not bound");
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaMemcpyAsync(out, h->error_word(), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return FFMP_OK;
+}
+
+int ffmp_op_scenarios(int32_t device, int32_t n, int32_t G, uint32_t p_thresh, int32_t goal_mode, int32_t block_shift,
+                      uint64_t seed, const uint32_t *env_gid_dev, const uint32_t *episode_dev, uint8_t *occ_dev,
+                      uint32_t *scen_dev, void *stream) {
+    if (n < 0 || !env_gid_dev || !episode_dev || !occ_dev || !scen_dev) return fail(FFMP_ERR_ARG, "bad argument");
+    if (G < 16 || G > 1024 || (G % 4)) return fail(FFMP_ERR_ARG, "G must be a multiple of 4 in [16,1024]");
+    if (int rc = check_device(device)) return rc;
+    DeviceGuard guard(device);
+    ffmp::ScenarioArgs a{};
+    a.env_gid = env_gid_dev; a.episode = episode_dev; a.count = n;
+    a.G = G; a.goal_mode = goal_mode; a.block_shift = block_shift; a.slot_mode = 0; a.S = 1; a.N = n;
+    a.p_thresh = p_thresh; a.seed = seed; a.occ = occ_dev; a.scen = scen_dev;
+    CK(ffmp::launch_scenarios(a, n < 148 * 8 ? n : 148 * 8, static_cast<cudaStream_t>(stream)));
+    return FFMP_OK;
+}
+
+size_t ffmp_op_flow_field_workspace(int32_t n, int32_t G) {
+    if (n <= 0 || !ffmp::flow_field_supported(G)) return 0;
+    const int maxg = ffmp::flow_field_max_grid(G);
+    return static_cast<size_t>(n < maxg ? n : maxg) * ffmp::flow_field_scratch_words(G) * 4;
+}
+
+int ffmp_op_flow_field(int32_t device, int32_t n, int32_t G, const uint8_t *occ_dev, const int32_t *goal_cells_dev,
+                       int32_t *cost_dev, uint8_t *flow_dev, void *workspace_dev, void *stream) {
+    if (n < 0 || !occ_dev || !goal_cells_dev || !flow_dev || !workspace_dev) return fail(FFMP_ERR_ARG, "bad argument");
+    if (!ffmp::flow_field_supported(G)) return fail(FFMP_ERR_ARG, "G must be a multiple of 4 in [16,128]");
+    if (reinterpret_cast<uintptr_t>(occ_dev) % 16 || reinterpret_cast<uintptr_t>(flow_dev) % 16 ||
+        reinterpret_cast<uintptr_t>(cost_dev) % 16)
+        return fail(FFMP_ERR_ARG, "occ / cost / flow must be 16-byte aligned");
+    if (int rc = check_device(device)) return rc;
+    DeviceGuard guard(device);
+    ffmp::FlowArgs a{};
+    a.count = n; a.G = G; a.slot_mode = 0; a.S = 1; a.N = n;
+    a.occ = occ_dev; a.goal_cells = goal_cells_dev; a.cost = cost_dev; a.flow = flow_dev;
+    a.hi_scratch = static_cast<uint32_t *>(workspace_dev);
+    const int maxg = ffmp::flow_field_max_grid(G);
+    CK(ffmp::launch_flow_field(a, n < maxg ? n : maxg, static_cast<cudaStream_t>(stream)));
+    return FFMP_OK;
+}
+
+static int run_rewarder(int32_t device, ffmp::RewarderArgs a, void *stream) {
+    if (a.n < 0 || !a.rel_goal || !a.is_first || !a.d_first || !a.reward || !a.done || !a.flags)
+        return fail(FFMP_ERR_ARG, "bad argument");
+    if (int rc = check_device(device)) return rc;
+    DeviceGuard guard(device);
+    CK(ffmp::launch_rewarder(a, static_cast<cudaStream_t>(stream)));
+    return FFMP_OK;
+}
+
+int ffmp_op_rewarder(int32_t device, int32_t n, int32_t W, const int32_t *local_map_dev, const float *rel_goal_dev,
+                     const uint8_t *is_first_dev, float *d_first_dev, float *reward_dev, uint8_t *done_dev,
+                     uint8_t *flags_dev, void *stream) {
+    if (W < 6 || !local_map_dev) return fail(FFMP_ERR_ARG, "bad argument");
+    ffmp::RewarderArgs a{};
+    a.n = n; a.W = W; a.local_map = local_map_dev; a.rel_goal = rel_goal_dev; a.is_first = is_first_dev;
+    a.d_first = d_first_dev; a.reward = reward_dev; a.done = done_dev; a.flags = flags_dev;
+    return run_rewarder(device, a, stream);
+}
+
+int ffmp_op_rewarder2(int32_t device, int32_t n, int32_t scan_len, const float *scan_dev, const float *rel_goal_dev,
+                      const uint8_t *is_first_dev, float *d_first_dev, float *reward_dev, uint8_t *done_dev,
+                      uint8_t *flags_dev, void *stream) {
+    if (scan_len < 0 || !scan_dev) return fail(FFMP_ERR_ARG, "bad argument");
+    ffmp::RewarderArgs a{};
+    a.n = n; a.scan = scan_dev; a.scan_len = scan_len; a.rel_goal = rel_goal_dev; a.is_first = is_first_dev;
+    a.d_first = d_first_dev; a.reward = reward_dev; a.done = done_dev; a.flags = flags_dev;
+    return run_rewarder(device, a, stream);
+}
+
+int ffmp_op_reward_calculator(int32_t device, int32_t n, const float *rel_goal_dev, const uint8_t *given_flags_dev,
+                              const uint8_t *is_first_dev, float *d_first_dev, float *reward_dev, uint8_t *done_dev,
+                              uint8_t *flags_dev, void *stream) {
+    if (!given_flags_dev) return fail(FFMP_ERR_ARG, "bad argument");
+    ffmp::RewarderArgs a{};
+    a.n = n; a.given_flags = given_flags_dev; a.rel_goal = rel_goal_dev; a.is_first = is_first_dev;
+    a.d_first = d_first_dev; a.reward = reward_dev; a.done = done_dev; a.flags = flags_dev;
+    return run_rewarder(device, a, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+// ffmp_common.cuh — constants, hash RNG and fp32 elementary functions shared by the sm_100a kernels.
+// Every function here implements one block of SPEC.md; fp32 code uses __f*_rn intrinsics so that no
+// FMA contraction can occur regardless of compiler flags (one rounding per written operation).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ffmp {
+
+constexpr float RES = 0.05f;
+constexpr float INV_RES = 20.0f;
+constexpr float PI_F = 3.14159274f;
+constexpr float TWO_PI_F = 6.28318548f;
+constexpr float PI_2_F = 1.57079637f;
+constexpr float PI_4_F = 0.785398185f;
+constexpr int COST_INF = 0x7FFFFFFF;
+constexpr uint32_t FULL = 0xFFFFFFFFu;
+
+constexpr uint32_t S_START = 0x53544152u;
+constexpr uint32_t S_GOAL = 0x474F414Cu;
+constexpr uint32_t S_YAW = 0x59415721u;
+
+// scenario record / state record word indices (include/ffmp_b200.h)
+enum { SC_X0 = 0, SC_Y0, SC_YAW0, SC_GX, SC_GY, SC_GI, SC_GJ, SC_KEY, SC_WORDS };
+enum { ST_X = 0, ST_Y, ST_YAW, ST_GX, ST_GY, ST_DFIRST, ST_RETURN, ST_STEPS, ST_EPISODE, ST_WORDS = 16 };
+
+// ---- SPEC.md §3 hash ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__host__ __device__ __forceinline__ uint32_t scenario_key(uint64_t seed, uint32_t env_gid, uint32_t episode) {
+    uint32_t k = mix32(static_cast<uint32_t>(seed) ^ 0x9E3779B9u);
+    k = mix32(k ^ static_cast<uint32_t>(seed >> 32));
+    k = mix32(k ^ env_gid);
+    k = mix32(k ^ episode);
+    return k;
+}
+__host__ __device__ __forceinline__ uint32_t draw(uint32_t key, uint32_t stream, uint32_t t) {
+    return mix32(mix32(key ^ stream) + t * 0x9E3779B1u);
+}
+
+// ---- SPEC.md §6 fp32 elementary functions --------------------------------------------------------
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+
+__device__ __forceinline__ float pi_to_pi(float a) {
+    while (a >= PI_F) a = fsub(a, TWO_PI_F);
+    while (a <= -PI_F) a = fadd(a, TWO_PI_F);
+    return a;
+}
+
+__device__ __forceinline__ void sincos_spec(float a, float &s, float &c) {
+    const float q = rintf(fmul(a, 0.636619747f));
+    float r = fsub(a, fmul(q, 1.5703125f));
+    r = fsub(r, fmul(q, 4.837512969970703125e-4f));
+    r = fsub(r, fmul(q, 7.54978995489188216e-8f));
+    const float z = fmul(r, r);
+    float sp = fmul(-1.9515295891e-4f, z);
+    sp = fadd(sp, 8.3321608736e-3f);
+    sp = fmul(sp, z);
+    sp = fsub(sp, 1.6666654611e-1f);
+    sp = fmul(sp, z);
+    sp = fmul(sp, r);
+    sp = fadd(sp, r);
+    float cp = fmul(2.443315711809948e-5f, z);
+    cp = fsub(cp, 1.388731625493765e-3f);
+    cp = fmul(cp, z);
+    cp = fadd(cp, 4.166664568298827e-2f);
+    cp = fmul(cp, z);
+    cp = fmul(cp, z);
+    cp = fsub(cp, fmul(0.5f, z));
+    cp = fadd(cp, 1.0f);
+    const int n = static_cast<int>(q) & 3;
+    if (n == 0) { s = sp; c = cp; }
+    else if (n == 1) { s = cp; c = -sp; }
+    else if (n == 2) { s = -sp; c = -cp; }
+    else { s = -cp; c = sp; }
+}
+
+__device__ __forceinline__ float atan2_spec(float y, float x) {
+    if (x == 0.0f && y == 0.0f) return 0.0f;
+    const float ax = fabsf(x), ay = fabsf(y);
+    const bool swap = ay > ax;
+    const float t = __fdiv_rn(swap ? ax : ay, swap ? ay : ax);
+    float base, u;
+    if (t > 0.414213568f) { base = PI_4_F; u = __fdiv_rn(fsub(t, 1.0f), fadd(t, 1.0f)); }
+    else { base = 0.0f; u = t; }
+    const float z = fmul(u, u);
+    float p = fmul(8.05374449538e-2f, z);
+    p = fsub(p, 1.38776856032e-1f);
+    p = fmul(p, z);
+    p = fadd(p, 1.99777106478e-1f);
+    p = fmul(p, z);
+    p = fsub(p, 3.33329491539e-1f);
+    p = fmul(p, z);
+    p = fmul(p, u);
+    p = fadd(p, u);
+    float a = fadd(base, p);
+    if (swap) a = fsub(PI_2_F, a);
+    if (x < 0.0f) a = fsub(PI_F, a);
+    if (y < 0.0f) a = -a;
+    return a;
+}
+
+__device__ __forceinline__ float dist_spec(float dx, float dy) {
+    return __fsqrt_rn(fadd(fmul(dx, dx), fmul(dy, dy)));
+}
+
+__device__ __forceinline__ int robot_cell(float x) {
+    return static_cast<int>(floorf(fadd(fmul(x, INV_RES), 0.5f)));
+}
+
+// SPEC.md §1 action table (robot/config.py:25-58)
+__device__ __forceinline__ void action_lookup(int a, float &v, float &w) {
+    const int iv = a / 7, iw = a - 7 * iv;
+    v = iv == 0 ? 0.0f : iv == 1 ? 0.2f : iv == 2 ? 0.4f : 0.6f;
+    w = iw == 0 ? -0.6f : iw == 1 ? -0.4f : iw == 2 ? -0.2f : iw == 3 ? 0.0f : iw == 4 ? 0.2f : iw == 5 ? 0.4f : 0.6f;
+}
+
+}  // namespace ffmp

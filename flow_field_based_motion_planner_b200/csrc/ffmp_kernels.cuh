@@ -1,0 +1,80 @@
+// ffmp_kernels.cuh — kernel argument blocks and launch entry points (internal to libffmp_b200.so).
+#pragma once
+#include "ffmp_common.cuh"
+
+namespace ffmp {
+
+// Work items: item -> (env, episode).  slot_mode=1: planes live at [(episode % S) * N + env] (env
+// batch with S resident scenario slots); slot_mode=0: planes live at [item] (stateless operators).
+struct ScenarioArgs {
+    const uint32_t *env_idx;    // dev u32[count] or null (env = item)
+    const uint32_t *env_gid;    // dev u32[count] or null (gid = env_id_base + env)
+    const uint32_t *episode;    // dev u32[count] or null (use episode_const)
+    const uint32_t *count_ptr;  // dev count or null (use `count`)
+    int count;
+    uint32_t episode_const;
+    int G, goal_mode, block_shift, slot_mode, S, N;
+    uint32_t p_thresh, env_id_base;
+    uint64_t seed;
+    uint8_t *occ;
+    uint32_t *scen;
+};
+
+struct FlowArgs {
+    const uint32_t *env_idx;    // dev u32[count] or null
+    const uint32_t *episode;    // dev u32[count] or null (use episode_const; slot_mode only)
+    const uint32_t *count_ptr;  // dev count or null
+    int count;
+    uint32_t episode_const;
+    int G, slot_mode, S, N;
+    const uint8_t *occ;
+    const int32_t *goal_cells;  // dev i32[count][2] (slot_mode=0)
+    const uint32_t *scen;       // scenario records (slot_mode=1: goal cell read from here)
+    int32_t *cost;              // may be null
+    uint8_t *flow;
+    uint32_t *hi_scratch;       // per-CTA spill area for cost bit-planes >= 8
+    uint32_t *ticket;           // dev u32: CTA completion ticket (slot_mode) or null
+    uint32_t *count_reset;      // dev u32 reset to 0 by the last CTA (the regen list counter) or null
+};
+
+struct StepArgs {
+    int N, G, W, K, S, max_steps;
+    float dt;
+    int mode;                   // 0 step, 1 masked reset, 2 begin-all (after full regeneration)
+    int slot_new;               // ring slot of the newest frame (older = slot_new-1)
+    int write_older;            // 1: every env also (re)writes the older frame
+    const int64_t *actions;     // dev i64[N] (mode 0)
+    const uint8_t *mask;        // dev u8[N] (mode 1)
+    const uint8_t *flow;        // [S][N][G][G]
+    const uint32_t *scen;       // [S][N][8]
+    uint32_t *state;            // [N][16]
+    uint8_t *frames;            // [N][K][W][W]
+    float *rel_goal, *velocity, *reward, *term_rel_goal, *term_velocity, *fin_return;
+    uint8_t *done, *flags;
+    int32_t *fin_length;
+    uint32_t *regen_env, *regen_episode, *regen_count;  // regeneration request list
+    uint32_t *error_word;
+};
+
+struct RewarderArgs {
+    int n, W;
+    const int32_t *local_map;   // map-based collision (ffmp.py:85-105) or null
+    const float *scan;          // LiDAR ranges f32[n][scan_len], NaN = None (ffmp.py:108-117) or null
+    int scan_len;
+    const uint8_t *given_flags; // explicit bit0 collision / bit1 goal (ffmp.py:130 signature) or null
+    const float *rel_goal;
+    const uint8_t *is_first;
+    float *d_first, *reward;
+    uint8_t *done, *flags;
+};
+
+// launchers (each returns the cudaError_t of the launch)
+cudaError_t launch_scenarios(const ScenarioArgs &a, int grid, cudaStream_t st);
+cudaError_t launch_flow_field(const FlowArgs &a, int grid, cudaStream_t st);
+cudaError_t launch_step(const StepArgs &a, cudaStream_t st);
+cudaError_t launch_rewarder(const RewarderArgs &a, cudaStream_t st);
+int flow_field_max_grid(int G);            // resident CTAs for a full wave (multiple of the SM count)
+size_t flow_field_scratch_words(int G);    // hi_scratch words per CTA
+bool flow_field_supported(int G);
+
+}  // namespace ffmp

@@ -1,0 +1,277 @@
+"""FFMPVectorEnv — batched, GPU-resident `FFMP-v0` with the reference's gym surface.
+
+Host side only: allocation of device buffers (torch), the ctypes calls into libffmp_b200.so and
+tensor views.  All arithmetic happens in the CUDA kernels (csrc/); there is no CPU fallback.
+
+Reference surface mirrored (paths under /root/reference/src/):
+  * spaces               gym_ffmp/envs/ffmp.py:28-64
+  * reward / done rules  gym_ffmp/envs/ffmp.py:85-188   (call site train.py:577)
+  * observation layout   train.py:474-486, 535-557      (maps NCHW oldest-first, rel goal, velocity)
+  * episode sequencing   train.py:559-565, 593, 607-608, 611-682
+  * gym (Dec 2020) API   reset() -> obs ; step(a) -> (obs, reward, done, info)
+"""
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import native, spaces
+from .robot import NUM_ACTIONS, RobotAction
+
+MAP_RANGE = 5.0          # ffmp.py:14
+MAP_GRID_NUM = 100       # ffmp.py:15
+MAP_RESOLUTION = 0.05    # ffmp.py:18
+ROBOT_RSIZE = 0.13       # ffmp.py:17
+GOAL_THRESHOLD = 0.5     # ffmp.py:19
+MAX_STEPS = 200          # train.py:60
+
+
+def p_threshold(p_occ: float) -> int:
+    """SPEC.md §3: min(2^32-1, floor(p_occ * 2^32)) in fp64."""
+    return int(min(4294967295, math.floor(float(p_occ) * 4294967296.0)))
+
+
+@dataclass
+class FFMPConfig:
+    num_envs: int = 1
+    grid: int = 128                 # G
+    window: int = MAP_GRID_NUM      # W (local map side)
+    ring: int = 8                   # K observation frame slots (2 = contiguous [N,2,W,W])
+    slots: int = 3                  # S resident scenario slots per env
+    max_steps: int = MAX_STEPS
+    goal_mode: int = 0              # 0 re-sampled per episode, 1 static at (G-8, G-8)
+    block_shift: int = 3
+    p_occ: float = 0.10
+    seed: int = 0
+    env_id_base: int = 0
+    dt: float = 0.1
+    device: str = "cuda:0"
+
+
+def make_spaces(window: int = MAP_GRID_NUM):
+    """Per-env spaces, equal to FFMP.__init__ (ffmp.py:28-64)."""
+    act = RobotAction()
+    action_low = np.array([act.cmd[0].linear_v, act.cmd[0].angular_v])
+    action_high = np.array([act.cmd[27].linear_v, act.cmd[27].angular_v])
+    action_space = spaces.Box(action_low, action_high, dtype=np.float32)
+    obs = {
+        "local_map": spaces.Box(np.full((window, window, 1), 0), np.full((window, window, 1), 255), dtype=np.int32),
+        "relative_goal": spaces.Box(np.array([0.0, 0.0]), np.array([math.sqrt(2.0) * MAP_RANGE, math.pi]), dtype=np.float32),
+        "velocity": spaces.Box(action_low, action_high, dtype=np.float32),
+    }
+    return action_space, spaces.Dict(obs), spaces.Dict(dict(obs))
+
+
+class FFMPVectorEnv:
+    """N independent FFMP environments stepped by one fused CUDA kernel per call."""
+
+    def __init__(self, num_envs=None, config: FFMPConfig = None, **kwargs):
+        cfg = config or FFMPConfig()
+        if num_envs is not None:
+            kwargs["num_envs"] = num_envs
+        if kwargs:
+            cfg = FFMPConfig(**{**cfg.__dict__, **kwargs})
+        self.config = cfg
+        self._L = native.lib()                      # raises if the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise native.NativeError("FFMPVectorEnv needs a CUDA device (B200); there is no CPU fallback")
+        self.device = torch.device(cfg.device)
+        if self.device.type != "cuda":
+            raise native.NativeError("FFMPVectorEnv device must be a CUDA device")
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", dev_index)
+        self.num_envs = cfg.num_envs
+        self.action_space, self.observation_space, self.state_space = make_spaces(cfg.window)
+        self.single_action_space, self.single_observation_space = self.action_space, self.observation_space
+        self.discrete_action_space = spaces.Discrete(NUM_ACTIONS)   # what the agent actually emits (train.py:70,345)
+        self.action = RobotAction()
+
+        c = native.Cfg(abi_version=native.ABI_VERSION, device=dev_index, num_envs=cfg.num_envs, grid=cfg.grid,
+                       window=cfg.window, ring=cfg.ring, slots=cfg.slots, max_steps=cfg.max_steps,
+                       goal_mode=cfg.goal_mode, block_shift=cfg.block_shift, p_thresh=p_threshold(cfg.p_occ),
+                       env_id_base=cfg.env_id_base, seed=cfg.seed, dt=cfg.dt, reserved=0)
+        self._cfg = c
+        sz = native.Sizes()
+        native.check(self._L.ffmp_query_sizes(C.byref(c), C.byref(sz)), "ffmp_query_sizes")
+        self._h = C.c_void_p()
+        native.check(self._L.ffmp_create(C.byref(c), C.byref(self._h)), "ffmp_create")
+
+        N, G, W, K, S = cfg.num_envs, cfg.grid, cfg.window, cfg.ring, cfg.slots
+        d = self.device
+        with torch.cuda.device(d):
+            self.occ = torch.zeros((S, N, G, G), dtype=torch.uint8, device=d)
+            self.cost = torch.zeros((S, N, G, G), dtype=torch.int32, device=d)
+            self.flow = torch.zeros((S, N, G, G), dtype=torch.uint8, device=d)
+            self.scen = torch.zeros((S, N, 8), dtype=torch.int32, device=d)
+            self.state = torch.zeros((N, 16), dtype=torch.int32, device=d)
+            self.frames = torch.zeros((N, K, W, W), dtype=torch.uint8, device=d)
+            self.rel_goal = torch.zeros((N, 2), dtype=torch.float32, device=d)
+            self.velocity = torch.zeros((N, 2), dtype=torch.float32, device=d)
+            self.reward = torch.zeros((N,), dtype=torch.float32, device=d)
+            self.done = torch.zeros((N,), dtype=torch.uint8, device=d)
+            self.flags = torch.zeros((N,), dtype=torch.uint8, device=d)
+            self.term_rel_goal = torch.zeros((N, 2), dtype=torch.float32, device=d)
+            self.term_velocity = torch.zeros((N, 2), dtype=torch.float32, device=d)
+            self.fin_return = torch.zeros((N,), dtype=torch.float32, device=d)
+            self.fin_length = torch.zeros((N,), dtype=torch.int32, device=d)
+            self._workspace = torch.zeros((sz.workspace,), dtype=torch.uint8, device=d)
+        assert self.occ.numel() == sz.occ and self.cost.numel() * 4 == sz.cost and self.frames.numel() == sz.frames
+        b = native.Buffers(**{name: getattr(self, name).data_ptr() for name in
+                              ("occ", "cost", "flow", "scen", "state", "frames", "rel_goal", "velocity", "reward",
+                               "done", "flags", "term_rel_goal", "term_velocity", "fin_return", "fin_length")},
+                           workspace=self._workspace.data_ptr())
+        native.check(self._L.ffmp_bind(self._h, C.byref(b)), "ffmp_bind")
+        self._done_bool = self.done.view(torch.bool)
+        self._views = {}
+        self._host = None
+        self._is_reset = False
+
+    # ------------------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _obs(self):
+        p = C.c_int32()
+        native.check(self._L.ffmp_obs_slot(self._h, C.byref(p)), "ffmp_obs_slot")
+        view = self._views.get(p.value)
+        if view is None:
+            view = self.frames.narrow(1, p.value - 1, 2)      # [N,2,W,W] = [older, newest] (train.py:474-486)
+            self._views[p.value] = view
+        return {"local_map": view, "relative_goal": self.rel_goal, "velocity": self.velocity}
+
+    def seed(self, seed=None):
+        """Re-seed; takes effect at the next full reset()."""
+        if seed is not None:
+            self.close()
+            self.__init__(config=FFMPConfig(**{**self.config.__dict__, "seed": int(seed)}))
+        return [self.config.seed]
+
+    def reset(self, mask=None):
+        """reset() restarts every env from episode 0 of its seed; reset(mask) starts the next episode of
+        the masked envs (bool/uint8 tensor on the device)."""
+        with torch.cuda.device(self.device):
+            if mask is None:
+                native.check(self._L.ffmp_reset(self._h, None, self._stream()), "ffmp_reset")
+                self._is_reset = True
+            else:
+                m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+                native.check(self._L.ffmp_reset(self._h, C.c_void_p(m.data_ptr()), self._stream()), "ffmp_reset(mask)")
+        return self._obs()
+
+    def step(self, actions):
+        """actions: int64[N] action ids on the device -> (obs, reward f32[N], done bool[N], info)."""
+        a = actions
+        if not (isinstance(a, torch.Tensor) and a.device == self.device and a.dtype == torch.int64 and a.is_contiguous()):
+            a = torch.as_tensor(a).to(device=self.device, dtype=torch.int64).contiguous()
+        if a.numel() != self.num_envs:
+            raise ValueError(f"expected {self.num_envs} actions, got {a.numel()}")
+        with torch.cuda.device(self.device):
+            native.check(self._L.ffmp_step(self._h, C.c_void_p(a.data_ptr()), self._stream()), "ffmp_step")
+        return self._obs(), self.reward, self._done_bool, self._info()
+
+    def _info(self):
+        return {"flags": self.flags, "terminal_relative_goal": self.term_rel_goal,
+                "terminal_velocity": self.term_velocity, "episode_return": self.fin_return,
+                "episode_length": self.fin_length}
+
+    @staticmethod
+    def decode_flags(flags):
+        return {"is_collision": (flags & 1) != 0, "is_goal": (flags & 2) != 0, "truncated": (flags & 4) != 0}
+
+    def rollout(self, actions):
+        """actions int64[T,N] on the device: T back-to-back steps with no host work in between."""
+        a = actions.contiguous()
+        assert a.dtype == torch.int64 and a.device == self.device and a.shape[1] == self.num_envs
+        with torch.cuda.device(self.device):
+            native.check(self._L.ffmp_rollout(self._h, C.c_void_p(a.data_ptr()), int(a.shape[0]), self._stream()), "ffmp_rollout")
+        return self._obs(), self.reward, self._done_bool, self._info()
+
+    def step_host(self, actions_host):
+        """Host-buffer step: actions int64[N] in (pinned) host memory -> (obs, reward, done, info) with reward,
+        done, flags, relative_goal and velocity returned as host tensors; local_map stays on the device."""
+        N = self.num_envs
+        if self._host is None:
+            pin = dict(pin_memory=True)
+            self._host = {"reward": torch.empty(N, dtype=torch.float32, **pin), "done": torch.empty(N, dtype=torch.uint8, **pin),
+                          "flags": torch.empty(N, dtype=torch.uint8, **pin), "rel_goal": torch.empty((N, 2), dtype=torch.float32, **pin),
+                          "velocity": torch.empty((N, 2), dtype=torch.float32, **pin)}
+        hst = self._host
+        a = actions_host
+        assert a.dtype == torch.int64 and a.device.type == "cpu" and a.numel() == N and a.is_contiguous()
+        with torch.cuda.device(self.device):
+            native.check(self._L.ffmp_step_host(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(hst["reward"].data_ptr()),
+                                                C.c_void_p(hst["done"].data_ptr()), C.c_void_p(hst["flags"].data_ptr()),
+                                                C.c_void_p(hst["rel_goal"].data_ptr()), C.c_void_p(hst["velocity"].data_ptr()),
+                                                self._stream()), "ffmp_step_host")
+        obs = self._obs()
+        obs = {"local_map": obs["local_map"], "relative_goal": hst["rel_goal"], "velocity": hst["velocity"]}
+        return obs, hst["reward"], hst["done"].view(torch.bool), {"flags": hst["flags"]}
+
+    @property
+    def h2d_bytes_per_step(self):
+        return self.num_envs * 8
+
+    @property
+    def d2h_bytes_per_step(self):
+        return self.num_envs * (4 + 1 + 1 + 8 + 8)
+
+    def join(self):
+        """Order the current stream after all queued background scenario regeneration."""
+        with torch.cuda.device(self.device):
+            native.check(self._L.ffmp_join(self._h, self._stream()), "ffmp_join")
+
+    def error_word(self) -> int:
+        w = C.c_uint32()
+        with torch.cuda.device(self.device):
+            native.check(self._L.ffmp_error_word(self._h, C.byref(w), self._stream()), "ffmp_error_word")
+        return w.value
+
+    # ---- inspection helpers (parity tests, debugging) ------------------------------------------
+    def pose(self):
+        return self.state[:, 0:3].view(torch.float32)
+
+    def goal(self):
+        return self.state[:, 3:5].view(torch.float32)
+
+    def episode(self):
+        return self.state[:, 8]
+
+    def steps(self):
+        return self.state[:, 7]
+
+    def _current(self, planes):
+        slot = (self.episode().to(torch.int64) % self.config.slots)
+        idx = torch.arange(self.num_envs, device=self.device)
+        return planes[slot, idx]
+
+    def cost_field(self):
+        """Integration field of every env's current scenario, int32 [N,G,G]."""
+        self.join()
+        return self._current(self.cost)
+
+    def flow_image(self):
+        self.join()
+        return self._current(self.flow)
+
+    def occupancy(self):
+        self.join()
+        return self._current(self.occ)
+
+    def flow_dir(self):
+        """Direction codes 0..7, 8 = none (SPEC.md §5 decoding of the flow image)."""
+        img = self.flow_image()
+        return torch.where(img == 255, torch.full_like(img, 8), img // 28)
+
+    def close(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._L.ffmp_destroy(h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,177 @@
+/*
+ * ffmp_b200.h — C-ABI of the B200-native gym_ffmp hot path (libffmp_b200.so).
+ *
+ * Plain C: pointers, sizes and PODs only (no torch / C++ types).  Every pointer marked "dev" is
+ * device memory allocated by the CALLER (e.g. a torch CUDA tensor); the library never frees it.
+ * Every `stream` argument is a cudaStream_t passed as void* (torch's current stream); the library
+ * never synchronises the host unless the function says so.  One host thread per GPU (one process
+ * per GPU under torchrun).  All functions return 0 on success or a negative ffmp_status; the text of
+ * the last failure on the calling thread is available from ffmp_last_error().  Nothing throws.
+ * There is NO CPU fallback: ffmp_create fails with FFMP_ERR_DEVICE if the device is not sm_100.
+ *
+ * Reference interfaces replaced (paths under /root/reference/):
+ *   - gym.make('FFMP-v0') -> FFMP object            src/train.py:456, src/gym_ffmp/__init__.py:3-6
+ *   - FFMP.rewarder / rewarder2 (per-tick reward)   src/gym_ffmp/envs/ffmp.py:167-188, call site src/train.py:577
+ *   - RobotAction.commander (action table)          src/gym_ffmp/envs/robot/config.py:25-58, src/train.py:668-669
+ *   - ROSNode geometry helpers                      src/train.py:157-188
+ *   - make_temporal_maps / obs assembly             src/train.py:474-486, 535-557
+ *   - external ROS producers the reference only subscribes to (flow image /bev/temporal_bev_image,
+ *     /odom physics, /start_goal_points scenario generator): src/train.py:84-90,116-143
+ * The frozen semantics of every entry point are in SPEC.md.
+ */
+#ifndef FFMP_B200_H
+#define FFMP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFMP_ABI_VERSION 1u
+#define FFMP_COST_INF 0x7FFFFFFF
+
+typedef enum ffmp_status {
+    FFMP_OK = 0,
+    FFMP_ERR_ARG = -1,      /* bad argument / unsupported configuration        */
+    FFMP_ERR_DEVICE = -2,   /* no CUDA device, or device is not sm_100          */
+    FFMP_ERR_CUDA = -3,     /* a CUDA runtime call failed (see ffmp_last_error) */
+    FFMP_ERR_STATE = -4,    /* call order violated (e.g. step before bind/reset) */
+    FFMP_ERR_ABI = -5       /* cfg.abi_version mismatch                          */
+} ffmp_status;
+
+typedef struct ffmp_handle ffmp_handle;
+
+/* Batched-environment configuration (defaults = the reference's constants, SPEC.md §1). */
+typedef struct ffmp_cfg {
+    uint32_t abi_version;  /* FFMP_ABI_VERSION */
+    int32_t device;        /* CUDA ordinal */
+    int32_t num_envs;      /* N: environments on this GPU */
+    int32_t grid;          /* G: global grid side, G%4==0, 16..1024            (reference map: 100, ffmp.py:15) */
+    int32_t window;        /* W: local map side, W%4==0, <= 256                (ffmp.py:15: 100) */
+    int32_t ring;          /* K >= 2 observation frame slots per env (SPEC.md §8) */
+    int32_t slots;         /* S >= 2 resident scenario slots per env (pre-generated episodes) */
+    int32_t max_steps;     /* truncation                                       (train.py:60: 200) */
+    int32_t goal_mode;     /* 0 goal re-sampled every episode, 1 static goal at (G-8,G-8) */
+    int32_t block_shift;   /* obstacle block = 2^block_shift cells */
+    uint32_t p_thresh;     /* floor(p_occ * 2^32) */
+    uint32_t env_id_base;  /* global id of local env 0 (multi-GPU sharding) */
+    uint64_t seed;
+    float dt;              /* integration step [s] */
+    uint32_t reserved;
+} ffmp_cfg;
+
+/* Byte sizes of every caller-allocated buffer for a given cfg (ffmp_query_sizes). */
+typedef struct ffmp_sizes {
+    size_t occ;            /* u8  [S][N][G][G]  occupancy planes                  */
+    size_t cost;           /* i32 [S][N][G][G]  integration field                 */
+    size_t flow;           /* u8  [S][N][G][G]  flow image (255 occ, else dir*28) */
+    size_t scen;           /* u32 [S][N][8]     scenario records                  */
+    size_t state;          /* u32 [N][16]       env state records                 */
+    size_t frames;         /* u8  [N][K][W][W]  observation frame ring            */
+    size_t vec2;           /* f32 [N][2]        rel_goal, velocity, term_*        */
+    size_t vec1;           /* 4B  [N]           reward, fin_return, fin_length    */
+    size_t bytes1;         /* u8  [N]           done, flags                       */
+    size_t workspace;      /* library scratch (regen lists, high cost bit-planes) */
+} ffmp_sizes;
+
+/* Scenario record layout (u32 words): 0 x0(f32) 1 y0 2 yaw0 3 gx 4 gy 5 gi(i32) 6 gj 7 hash key.
+ * State record layout (u32 words): 0 x 1 y 2 yaw 3 gx 4 gy 5 d_first 6 ep_return (all f32)
+ *                                  7 steps(i32) 8 episode(u32) 9..15 reserved. */
+typedef struct ffmp_buffers {
+    uint8_t *occ;              /* dev */
+    int32_t *cost;             /* dev */
+    uint8_t *flow;             /* dev */
+    uint32_t *scen;            /* dev */
+    uint32_t *state;           /* dev */
+    uint8_t *frames;           /* dev: observation local_map ring */
+    float *rel_goal;           /* dev f32[N][2]: [dist, bearing]             (train.py:174-180) */
+    float *velocity;           /* dev f32[N][2]: [|dxy|, wrap(dyaw)]         (train.py:182-188) */
+    float *reward;             /* dev f32[N]                                 (ffmp.py:130-157)  */
+    uint8_t *done;             /* dev u8[N]: collision | goal | truncated    (ffmp.py:160-164, train.py:607-608) */
+    uint8_t *flags;            /* dev u8[N]: bit0 collision bit1 goal bit2 truncated */
+    float *term_rel_goal;      /* dev f32[N][2]: pre-reset values of the step just taken */
+    float *term_velocity;      /* dev f32[N][2] */
+    float *fin_return;         /* dev f32[N]: episode return, valid where done */
+    int32_t *fin_length;       /* dev i32[N]: episode length, valid where done */
+    void *workspace;           /* dev, ffmp_sizes.workspace bytes, zero-initialised by the caller */
+} ffmp_buffers;
+
+const char *ffmp_last_error(void);
+uint32_t ffmp_abi_version(void);
+
+int ffmp_query_sizes(const ffmp_cfg *cfg, ffmp_sizes *out);
+int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out);
+int ffmp_bind(ffmp_handle *h, const ffmp_buffers *bufs);
+int ffmp_destroy(ffmp_handle *h);
+
+/* reset: mask_dev == NULL -> every env restarts from episode 0 (all S scenario slots are generated,
+ * flow fields included, on `stream`).  Otherwise masked envs (mask != 0) abandon their episode and
+ * start their next one (same path as an auto-reset).  Observation outputs are written.            */
+int ffmp_reset(ffmp_handle *h, const uint8_t *mask_dev, void *stream);
+
+/* step: actions_dev = i64[N] ids in [0,28) (SPEC.md §1).  Writes every output buffer, auto-resets
+ * finished envs, and queues the regeneration of their consumed scenario slot on an internal
+ * background stream.  Replaces the per-tick body of train.py:531-682.                             */
+int ffmp_step(ffmp_handle *h, const int64_t *actions_dev, void *stream);
+
+/* T back-to-back steps with actions_dev = i64[T][N]; identical to T ffmp_step calls. */
+int ffmp_rollout(ffmp_handle *h, const int64_t *actions_dev, int32_t T, void *stream);
+
+/* Host-buffer step (the reference-facing call with HOST memory): copies actions_host (i64[N], ideally
+ * pinned) to the device, steps, copies reward f32[N], done u8[N], flags u8[N], rel_goal f32[N][2] and
+ * velocity f32[N][2] back (any out pointer may be NULL) and synchronises `stream`.  The local_map
+ * observation stays on the device.                                                                  */
+int ffmp_step_host(ffmp_handle *h, const int64_t *actions_host, float *reward_host, uint8_t *done_host,
+                   uint8_t *flags_host, float *rel_goal_host, float *velocity_host, void *stream);
+
+/* Index of the newest frame slot p (1 <= p <= K-1): the observation is frames[:, p-1 : p+1]. */
+int ffmp_obs_slot(const ffmp_handle *h, int32_t *newest_slot);
+
+/* Make `stream` wait (device-side, no host sync) for all queued background regeneration. */
+int ffmp_join(ffmp_handle *h, void *stream);
+
+/* Device error word accumulated by the kernels (bit0: action id out of range). Synchronises `stream`. */
+int ffmp_error_word(ffmp_handle *h, uint32_t *out, void *stream);
+
+/* ---- stateless operators (what the reference's external ROS nodes computed) ------------------- */
+
+/* Scenario generator (SPEC.md §3): for item n, env id env_gid_dev[n] (u32) and episode episode_dev[n]
+ * (u32) -> occ u8[n][G][G], scen u32[n][8].  Replaces the external episode_manager node
+ * (train.py:86-90,128-132).                                                                        */
+int ffmp_op_scenarios(int32_t device, int32_t n, int32_t G, uint32_t p_thresh, int32_t goal_mode, int32_t block_shift,
+                      uint64_t seed, const uint32_t *env_gid_dev, const uint32_t *episode_dev, uint8_t *occ_dev,
+                      uint32_t *scen_dev, void *stream);
+
+/* Flow field (SPEC.md §4,§5): occ u8[n][G][G] + goal cells i32[n][2] -> cost i32[n][G][G] (may be NULL),
+ * flow u8[n][G][G].  workspace_dev: ffmp_op_flow_field_workspace(n,G) bytes.  Replaces the external
+ * /bev/* flow-image node (train.py:84,116-121).                                                    */
+size_t ffmp_op_flow_field_workspace(int32_t n, int32_t G);
+int ffmp_op_flow_field(int32_t device, int32_t n, int32_t G, const uint8_t *occ_dev, const int32_t *goal_cells_dev,
+                       int32_t *cost_dev, uint8_t *flow_dev, void *workspace_dev, void *stream);
+
+/* Batched FFMP.rewarder (ffmp.py:167-176) on caller-supplied ego-centred local maps:
+ * local_map i32[n][W][W] (>0 = occupied, robot at (W/2,W/2)), rel_goal f32[n][2], is_first u8[n],
+ * d_first f32[n] (in/out latch, per item instead of the reference's module global)
+ * -> reward f32[n], done u8[n], flags u8[n] (bit0 collision, bit1 goal).                           */
+int ffmp_op_rewarder(int32_t device, int32_t n, int32_t W, const int32_t *local_map_dev, const float *rel_goal_dev,
+                     const uint8_t *is_first_dev, float *d_first_dev, float *reward_dev, uint8_t *done_dev,
+                     uint8_t *flags_dev, void *stream);
+
+/* Batched FFMP.rewarder2 (ffmp.py:179-188, the variant train.py:577 calls): scan f32[n][scan_len] LiDAR
+ * ranges, NaN = None; collision iff a non-zero range is < 0.13 (ffmp.py:108-117).                  */
+int ffmp_op_rewarder2(int32_t device, int32_t n, int32_t scan_len, const float *scan_dev, const float *rel_goal_dev,
+                      const uint8_t *is_first_dev, float *d_first_dev, float *reward_dev, uint8_t *done_dev,
+                      uint8_t *flags_dev, void *stream);
+
+/* Batched FFMP.reward_calculator (ffmp.py:130-157): collision / goal given explicitly in given_flags
+ * (bit0 collision, bit1 goal).                                                                      */
+int ffmp_op_reward_calculator(int32_t device, int32_t n, const float *rel_goal_dev, const uint8_t *given_flags_dev,
+                              const uint8_t *is_first_dev, float *d_first_dev, float *reward_dev, uint8_t *done_dev,
+                              uint8_t *flags_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFMP_B200_H */

@@ -1,0 +1,348 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle on identical
+seeded inputs.  Integer / byte work is bit-exact; the fp32 SPEC (fixed operation order, no FMA) makes
+poses, rewards and observations bit-exact too, which is stricter than the 1e-5 tolerance of the
+north star (asserted as well so a future relaxation stays visible)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from maps import special_cases
+
+pytestmark = pytest.mark.gpu
+
+INF = oracle.INF
+
+
+@pytest.fixture(scope="module")
+def ffmp(cuda_device):
+    import flow_field_based_motion_planner_b200 as pkg
+    return pkg
+
+
+def t2n(t):
+    return t.detach().cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------
+# M: scenario generator
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("G,mode,bs,p", [(128, 0, 3, 0.1), (64, 1, 3, 0.1), (100, 0, 0, 0.1), (32, 0, 2, 0.3),
+                                         (128, 1, 4, 0.25), (16, 0, 1, 0.2), (96, 0, 3, 0.1)])
+def test_scenarios_bit_exact(ffmp, cuda_device, G, mode, bs, p):
+    n = 24
+    gids = torch.arange(1000, 1000 + n, device=cuda_device)
+    eps = torch.arange(n, device=cuda_device) % 5
+    occ, scen = ffmp.ops.generate_scenarios(gids, eps, G, p_occ=p, goal_mode=mode, block_shift=bs, seed=0xABCDEF0123)
+    occ, scen = t2n(occ), t2n(scen)
+    for k in range(n):
+        o, start, goal, cells = oracle.scenario(0xABCDEF0123, 1000 + k, k % 5, G, p_occ=p, goal_mode=mode, block_shift=bs)
+        assert np.array_equal(occ[k], o), (k, "occ")
+        rec = scen[k]
+        assert np.array_equal(rec[0:3].view(np.float32), start)
+        assert np.array_equal(rec[3:5].view(np.float32), goal)
+        assert rec[5:7].tolist() == cells[2:4].tolist()
+        assert np.uint32(rec[7]) == np.uint32(oracle.lib().orc_key(0xABCDEF0123, 1000 + k, k % 5))
+
+
+# ---------------------------------------------------------------------------------------------------
+# F1 + F2: integration field and flow direction
+# ---------------------------------------------------------------------------------------------------
+def run_flow(ffmp, dev, occs, goals, want_cost=True):
+    occ_t = torch.as_tensor(np.stack(occs), device=dev)
+    goal_t = torch.as_tensor(np.array(goals, np.int32), device=dev)
+    cost, flow = ffmp.ops.flow_field(occ_t, goal_t, want_cost=want_cost)
+    torch.cuda.synchronize()
+    return (t2n(cost) if want_cost else None), t2n(flow)
+
+
+@pytest.mark.parametrize("G", [16, 32, 64, 96, 100, 128])
+def test_flow_field_special_maps_bit_exact(ffmp, cuda_device, G):
+    cases = special_cases(G)
+    cost, flow = run_flow(ffmp, cuda_device, [c[1] for c in cases], [c[2] for c in cases])
+    for k, (name, occ, goal) in enumerate(cases):
+        ec, ed, ef = oracle.flow_field(occ, goal[0], goal[1])
+        assert np.array_equal(cost[k], ec), (G, name, "cost", int((cost[k] != ec).sum()))
+        assert np.array_equal(flow[k], ef), (G, name, "flow", int((flow[k] != ef).sum()))
+        d = np.where(flow[k] == 255, 8, flow[k] // 28)
+        assert np.array_equal(d, ed), (G, name, "dir")
+
+
+@pytest.mark.parametrize("G,bs,p", [(128, 3, 0.1), (128, 0, 0.3), (64, 3, 0.1), (128, 2, 0.35), (100, 3, 0.2)])
+def test_flow_field_generated_maps_bit_exact(ffmp, cuda_device, G, bs, p):
+    n = 96
+    occs, goals = [], []
+    for k in range(n):
+        o, _, _, cells = oracle.scenario(99, k, 0, G, p_occ=p, block_shift=bs)
+        occs.append(o)
+        goals.append((cells[2], cells[3]))
+    cost, flow = run_flow(ffmp, cuda_device, occs, goals)
+    for k in range(n):
+        ec, ed, ef = oracle.flow_field(occs[k], *goals[k])
+        assert np.array_equal(cost[k], ec), (k, "cost")
+        assert np.array_equal(flow[k], ef), (k, "flow")
+
+
+def test_flow_field_without_cost_output(ffmp, cuda_device):
+    occs, goals = [], []
+    for k in range(8):
+        o, _, _, cells = oracle.scenario(5, k, 0, 128)
+        occs.append(o); goals.append((cells[2], cells[3]))
+    _, flow = run_flow(ffmp, cuda_device, occs, goals, want_cost=False)
+    for k in range(8):
+        assert np.array_equal(flow[k], oracle.flow_field(occs[k], *goals[k])[2])
+
+
+def test_flow_field_empty_batch(ffmp, cuda_device):
+    cost, flow = ffmp.ops.flow_field(torch.zeros((0, 64, 64), dtype=torch.uint8, device=cuda_device),
+                                     torch.zeros((0, 2), dtype=torch.int32, device=cuda_device))
+    assert cost.shape == (0, 64, 64) and flow.shape == (0, 64, 64)
+
+
+def test_flow_field_full_size_properties(ffmp, cuda_device):
+    """BASELINE config 3 size (4096 x 128 x 128): size-independent properties on the device, plus an
+    oracle check of a sample."""
+    n, G = 4096, 128
+    dev = cuda_device
+    gids = torch.arange(n, device=dev)
+    occ, scen = ffmp.ops.generate_scenarios(gids, torch.zeros_like(gids), G, seed=2024)
+    goals = scen[:, 5:7].contiguous()
+    cost, flow = ffmp.ops.flow_field(occ, goals)
+    torch.cuda.synchronize()
+    c = cost.to(torch.int64)
+    reach = c != INF
+    idx = torch.arange(n, device=dev)
+    assert (c[idx, goals[:, 0].long(), goals[:, 1].long()] == 0).all()
+    assert (c[occ != 0] == INF).all()
+    big = torch.full((n, G + 2, G + 2), INF, dtype=torch.int64, device=dev)
+    big[:, 1:-1, 1:-1] = c
+    nmin = torch.minimum(torch.minimum(big[:, :-2, 1:-1], big[:, 2:, 1:-1]), torch.minimum(big[:, 1:-1, :-2], big[:, 1:-1, 2:]))
+    inner = reach.clone()
+    inner[idx, goals[:, 0].long(), goals[:, 1].long()] = False
+    assert (nmin[inner] == c[inner] - 1).all()
+    lost = (occ == 0) & ~reach
+    assert (nmin[lost] == INF).all()
+    # flow image: occupied <-> 255, reached non-goal cells always have a direction, others "none"
+    assert ((flow == 255) == (occ != 0)).all()
+    d = torch.where(flow == 255, torch.full_like(flow, 8), flow // 28)
+    assert (d[inner] < 8).all() and (d[~inner] == 8).all()
+    # the chosen neighbour is strictly lower: cost[n] == cost - 1 (orthogonal) or cost - 2 (diagonal)
+    DI = torch.tensor([1, 1, 0, -1, -1, -1, 0, 1, 0], device=dev)
+    DJ = torch.tensor([0, 1, 1, 1, 0, -1, -1, -1, 0], device=dev)
+    ii, jj = torch.meshgrid(torch.arange(G, device=dev), torch.arange(G, device=dev), indexing="ij")
+    ni = (ii[None] + DI[d.long()]).clamp(0, G - 1)
+    nj = (jj[None] + DJ[d.long()]).clamp(0, G - 1)
+    nc = c[idx[:, None, None], ni, nj]
+    drop = torch.where(d % 2 == 1, 2, 1)
+    assert (nc[inner] == (c - drop)[inner]).all()
+    occ_n, cost_n, flow_n = t2n(occ), t2n(cost), t2n(flow)
+    for k in range(0, n, 97):
+        ec, _, ef = oracle.flow_field(occ_n[k], int(goals[k, 0]), int(goals[k, 1]))
+        assert np.array_equal(cost_n[k], ec) and np.array_equal(flow_n[k], ef), k
+
+
+# ---------------------------------------------------------------------------------------------------
+# step()/reset(): full env rollouts
+# ---------------------------------------------------------------------------------------------------
+def compare_env(env, orc, t, check_planes=False):
+    obs = env._obs()
+    assert np.array_equal(t2n(obs["local_map"]), orc.local_map), (t, "local_map")
+    for name, got, exp in [("rel_goal", env.rel_goal, orc.rel_goal), ("velocity", env.velocity, orc.velocity),
+                           ("pose", env.pose(), orc.pose), ("goal", env.goal(), orc.goal)]:
+        g = t2n(got)
+        assert np.allclose(g, exp, rtol=1e-5, atol=1e-6), (t, name)          # north-star tolerance
+        assert np.array_equal(g.view(np.uint32), exp.view(np.uint32)), (t, name, "bit-exact")
+    assert np.array_equal(t2n(env.episode()).astype(np.uint32), orc.episode), (t, "episode")
+    assert np.array_equal(t2n(env.steps()), orc.steps), (t, "steps")
+    if check_planes:
+        assert np.array_equal(t2n(env.cost_field()), orc.cost), (t, "cost")
+        assert np.array_equal(t2n(env.flow_image()), orc.flow), (t, "flow")
+        assert np.array_equal(t2n(env.occupancy()), orc.occ), (t, "occ")
+        assert np.array_equal(t2n(env.flow_dir()), orc.dir), (t, "dir")
+
+
+def rollout_parity(ffmp, N, steps, seed=0, check_every=50, **kw):
+    env = ffmp.FFMPVectorEnv(N, seed=seed, **kw)
+    okw = {k: v for k, v in kw.items() if k in ("grid", "window", "max_steps", "goal_mode", "p_occ", "block_shift", "env_id_base", "dt")}
+    orc = oracle.OracleVectorEnv(N, seed=seed, **okw)
+    env.reset()
+    orc.reset()
+    compare_env(env, orc, -1, check_planes=True)
+    rng = np.random.default_rng(seed + 1)
+    ndone = 0
+    for t in range(steps):
+        a = rng.integers(0, 28, N)
+        _, reward, done, info = env.step(torch.as_tensor(a, device=env.device))
+        orc.step(a)
+        r = t2n(reward)
+        assert np.allclose(r, orc.reward, rtol=1e-5, atol=1e-7), (t, "reward tol")
+        assert np.array_equal(r.view(np.uint32), orc.reward.view(np.uint32)), (t, "reward")
+        assert np.array_equal(t2n(done).astype(np.uint8), orc.done), (t, "done")
+        assert np.array_equal(t2n(info["flags"]), orc.flags), (t, "flags")
+        assert np.array_equal(t2n(info["terminal_relative_goal"]).view(np.uint32), orc.term_rel_goal.view(np.uint32)), t
+        assert np.array_equal(t2n(info["terminal_velocity"]).view(np.uint32), orc.term_velocity.view(np.uint32)), t
+        d = orc.done.astype(bool)
+        if d.any():
+            assert np.array_equal(t2n(info["episode_return"])[d].view(np.uint32), orc.fin_return[d].view(np.uint32)), t
+            assert np.array_equal(t2n(info["episode_length"])[d], orc.fin_length[d]), t
+        ndone += int(d.sum())
+        compare_env(env, orc, t, check_planes=(t % check_every == check_every - 1))
+    assert env.error_word() == 0
+    env.close()
+    return ndone
+
+
+def test_rollout_1k_steps_config3_shape(ffmp):
+    """1k-step random-action rollout, 128x128 grids, W=100, goal re-sampled per reset (config 3 per-env shape)."""
+    ndone = rollout_parity(ffmp, 48, 1000, seed=0, grid=128, window=100, check_every=100)
+    assert ndone > 200            # many auto-resets (and background regenerations) were exercised
+
+
+def test_rollout_config2_static_goal(ffmp):
+    rollout_parity(ffmp, 64, 400, seed=3, grid=64, window=64, goal_mode=1, check_every=100)
+
+
+def test_rollout_config1_default_grid(ffmp):
+    """config 1: one env, the reference's 100x100 grid (ffmp.py:15), 1k random steps."""
+    rollout_parity(ffmp, 1, 1000, seed=0, grid=100, window=100, check_every=250)
+
+
+@pytest.mark.parametrize("ring,slots", [(2, 3), (3, 2), (5, 4), (8, 3)])
+def test_rollout_ring_and_slot_variants(ffmp, ring, slots):
+    rollout_parity(ffmp, 32, 150, seed=7, grid=64, window=32, ring=ring, slots=slots, max_steps=12, check_every=30)
+
+
+def test_rollout_dense_obstacles_short_episodes(ffmp):
+    """p=0.3 per-cell noise: episodes of a few steps, so nearly every step regenerates slots."""
+    rollout_parity(ffmp, 32, 200, seed=9, grid=128, window=100, p_occ=0.3, block_shift=0, check_every=50)
+
+
+def test_sharded_env_ids(ffmp):
+    """Two shards (env_id_base 0 and 8) reproduce one batch of 16: results depend on global ids only."""
+    rollout_parity(ffmp, 8, 60, seed=21, grid=64, window=32, env_id_base=8, check_every=30)
+
+
+def test_masked_reset(ffmp, cuda_device):
+    N = 16
+    env = ffmp.FFMPVectorEnv(N, seed=4, grid=64, window=32)
+    orc = oracle.OracleVectorEnv(N, seed=4, grid=64, window=32)
+    env.reset(); orc.reset()
+    rng = np.random.default_rng(0)
+    for t in range(40):
+        a = rng.integers(0, 28, N)
+        env.step(torch.as_tensor(a, device=cuda_device)); orc.step(a)
+        if t % 7 == 3:
+            m = rng.random(N) < 0.4
+            env.reset(torch.as_tensor(m, device=cuda_device)); orc.reset(m)
+        compare_env(env, orc, t, check_planes=(t % 10 == 9))
+    # a second full reset restarts from episode 0 with identical results
+    first = {k: t2n(v).copy() for k, v in env.reset().items()}
+    orc.reset()
+    compare_env(env, orc, 100, check_planes=True)
+    again = {k: t2n(v).copy() for k, v in env.reset().items()}
+    for k in first:
+        assert np.array_equal(first[k], again[k])
+    env.close()
+
+
+def test_rollout_api_and_host_step(ffmp, cuda_device):
+    N, T = 32, 25
+    env = ffmp.FFMPVectorEnv(N, seed=12, grid=64, window=32)
+    orc = oracle.OracleVectorEnv(N, seed=12, grid=64, window=32)
+    env.reset(); orc.reset()
+    rng = np.random.default_rng(5)
+    acts = rng.integers(0, 28, (T, N))
+    env.rollout(torch.as_tensor(acts, device=cuda_device))
+    for t in range(T):
+        orc.step(acts[t])
+    compare_env(env, orc, T)
+    host_a = torch.as_tensor(rng.integers(0, 28, N)).pin_memory()
+    obs, reward, done, info = env.step_host(host_a)
+    orc.step(host_a.numpy())
+    assert reward.device.type == "cpu" and np.array_equal(reward.numpy().view(np.uint32), orc.reward.view(np.uint32))
+    assert np.array_equal(done.numpy().astype(np.uint8), orc.done)
+    assert np.array_equal(obs["relative_goal"].numpy().view(np.uint32), orc.rel_goal.view(np.uint32))
+    assert np.array_equal(t2n(obs["local_map"]), orc.local_map)
+    env.close()
+
+
+def test_invalid_actions_and_errors(ffmp, cuda_device):
+    env = ffmp.FFMPVectorEnv(4, seed=1, grid=64, window=32)
+    with pytest.raises(ffmp.native.NativeError):
+        env.step(torch.zeros(4, dtype=torch.int64, device=cuda_device))       # step before reset
+    env.reset()
+    env.step(torch.tensor([3, 99, -5, 27], device=cuda_device))
+    assert env.error_word() & 1
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(5, dtype=torch.int64, device=cuda_device))
+    env.close()
+    with pytest.raises(ffmp.native.NativeError):
+        ffmp.FFMPVectorEnv(4, grid=512)                                         # unsupported in this build
+    with pytest.raises(ffmp.native.NativeError):
+        ffmp.FFMPVectorEnv(4, window=50)
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference surface: FFMP compat object against the reference's golden answers
+# ---------------------------------------------------------------------------------------------------
+def test_compat_object_against_reference_golden(ffmp, golden):
+    env = ffmp.make("FFMP-v0")
+    for case in golden["is_collision"]:
+        m = np.zeros((100, 100), np.int32)
+        for (i, j) in case["cells"]:
+            m[i, j] = case["value"]
+        assert env.is_collision(m) == case["expect"], case
+    for case in golden["is_collision2"]:
+        assert env.is_collision2(case["scan"]) == case["expect"], case
+    for case in golden["is_goal"]:
+        if abs(case["d"] - 0.5) > 1e-6:                       # fp32 cannot resolve 0.5 +- 1e-7
+            assert env.is_goal(case["d"]) == case["expect"], case
+    assert env.is_goal(0.5) is False and env.is_goal(0.49) is True
+    for case in golden["is_done"]:
+        assert env.is_done(case["col"], case["goal"]) == case["expect"]
+    for seq in golden["reward_sequences"]:
+        for s in seq:
+            got = env.reward_calculator([s["d"], 0.0], s["col"], s["goal"], s["is_first"])
+            assert abs(got - s["expect"]) <= 1e-5 * max(1.0, abs(s["expect"])), s
+    for case in golden["rewarder"]:
+        m = np.zeros((100, 100), np.int32)
+        for (i, j) in case["cells"]:
+            m[i, j] = 255
+        r, d = env.rewarder(m, case["rel_goal"], case["is_first"])
+        assert abs(r - case["expect"][0]) <= 1e-5 and d == case["expect"][1], case
+    for case in golden["rewarder2"]:
+        r, d, g = env.rewarder2(case["scan"], case["rel_goal"], case["is_first"])
+        assert abs(r - case["expect"][0]) <= 1e-5 and [d, g] == case["expect"][1:], case
+
+
+def test_env_collision_equals_reference_is_collision_on_crop(ffmp, cuda_device):
+    """The env's footprint test on the global grid == FFMP.is_collision on the ego-centred occupancy crop
+    (reference footprint pinned by tests/golden)."""
+    N = 64
+    env = ffmp.FFMPVectorEnv(N, seed=33, grid=128, window=100, ring=2)
+    env.reset()
+    rng = np.random.default_rng(1)
+    L = oracle.lib()
+    import ctypes as C
+    checked = 0
+    for t in range(60):
+        a = rng.integers(7, 28, N)
+        pose_before = t2n(env.pose()).copy()
+        occ_before = t2n(env.occupancy()).copy()
+        _, _, done, info = env.step(torch.as_tensor(a, device=cuda_device))
+        flags = t2n(info["flags"])
+        # rebuild the occupancy crop at the pose the step evaluated (terminal pose for finished envs)
+        for e in range(N):
+            v, w = [(c.linear_v, c.angular_v) for c in [env.action.commander(int(a[e]))]][0]
+            x, y, yaw = pose_before[e]
+            s, c = oracle.sincos(yaw)
+            nx = np.float32(x + np.float32(np.float32(np.float32(v) * c) * np.float32(0.1)))
+            ny = np.float32(y + np.float32(np.float32(np.float32(v) * s) * np.float32(0.1)))
+            ci = int(np.floor(np.float32(nx * np.float32(20.0)) + np.float32(0.5)))
+            cj = int(np.floor(np.float32(ny * np.float32(20.0)) + np.float32(0.5)))
+            crop = oracle.crop(np.where(occ_before[e] != 0, 255, 0).astype(np.uint8), 100, ci, cj).astype(np.int32)
+            ref = L.orc_ref_is_collision(crop.ctypes.data_as(C.POINTER(C.c_int32)), 100, 0.05, 5.0, 0.13)
+            assert bool(ref) == bool(flags[e] & 1), (t, e)
+            checked += 1
+    assert checked == 60 * N
+    env.close()
