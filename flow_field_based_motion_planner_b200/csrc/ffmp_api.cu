@@ -39,21 +39,27 @@ struct DeviceGuard {
 };
 
 constexpr int MAX_LISTS = 7;
+constexpr int REGEN_GRID = 148 * 4;   // CTAs of a background regeneration launch
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int check_device(int device) {
+    // cudaGetDeviceProperties costs milliseconds: the verdict is cached per ordinal
+    static int verdict[64] = {0};   // 0 unknown, 1 ok
+    if (device >= 0 && device < 64 && verdict[device] == 1) return FFMP_OK;
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
         cudaGetLastError();
         return fail(FFMP_ERR_DEVICE, "no CUDA device available (there is no CPU fallback)");
     }
     if (device < 0 || device >= n) return fail(FFMP_ERR_DEVICE, "device ordinal out of range");
-    cudaDeviceProp prop;
-    cudaError_t ce = cudaGetDeviceProperties(&prop, device);
-    if (ce != cudaSuccess) return fail(FFMP_ERR_CUDA, "cudaGetDeviceProperties", ce);
-    if (prop.major != 10 || prop.minor != 0)
+    int major = 0, minor = 0;
+    cudaError_t ce = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
+    if (ce != cudaSuccess) return fail(FFMP_ERR_CUDA, "cudaDeviceGetAttribute", ce);
+    if (major != 10 || minor != 0)
         return fail(FFMP_ERR_DEVICE, "device is not sm_100 (B200); this library carries sm_100a code only");
+    if (device < 64) verdict[device] = 1;
     return FFMP_OK;
 }
 
@@ -74,7 +80,7 @@ int check_cfg(const ffmp_cfg *c) {
 }
 
 struct Workspace {
-    size_t error_word, lists, actions, hi, total;
+    size_t error_word, lists, actions, obs_order, hi, total;
     size_t list_stride;  // bytes per regen list block: [count,ticket,pad..64B][env u32 N][episode u32 N]
 };
 
@@ -86,8 +92,10 @@ Workspace workspace_layout(const ffmp_cfg *c) {
     w.list_stride = align_up(256 + 2 * N * sizeof(uint32_t), 256);
     w.lists = off; off += w.list_stride * static_cast<size_t>(c->slots - 1);
     w.actions = off; off += align_up(N * sizeof(int64_t), 256);
+    w.obs_order = off; off += align_up(N * 8 * sizeof(uint32_t), 256);
     w.hi = off;
-    off += align_up(static_cast<size_t>(ffmp::flow_field_max_grid(c->grid)) * ffmp::flow_field_scratch_words(c->grid) * 4, 256);
+    off += align_up((static_cast<size_t>(ffmp::flow_field_max_grid(c->grid)) + static_cast<size_t>(c->slots - 1) * REGEN_GRID) *
+                        ffmp::flow_field_scratch_words(c->grid) * 4, 256);
     w.total = off;
     return w;
 }
@@ -99,13 +107,14 @@ struct ffmp_handle {
     ffmp_buffers b;
     Workspace ws;
     bool bound = false, ready = false;
-    cudaStream_t side = nullptr;
+    cudaStream_t side[MAX_LISTS];   // one background stream per regeneration list: regenerations overlap
     int nlist = 1;
     cudaEvent_t ev_step[MAX_LISTS], ev_regen[MAX_LISTS];
     bool regen_pending[MAX_LISTS];
     uint64_t step_index = 0;
     int p = 1;  // newest ring slot
-    int ff_grid = 0, sc_grid = 0;
+    int ff_grid = 0, sc_grid = 0;   // full-batch grids (reset)
+    int rg_grid = 0;                // background regeneration grid (few items per tick)
 
     uint32_t *error_word() const { return reinterpret_cast<uint32_t *>(static_cast<char *>(b.workspace) + ws.error_word); }
     char *list_base(int l) const { return static_cast<char *>(b.workspace) + ws.lists + ws.list_stride * l; }
@@ -114,6 +123,7 @@ struct ffmp_handle {
     uint32_t *list_env(int l) const { return reinterpret_cast<uint32_t *>(list_base(l) + 256); }
     uint32_t *list_episode(int l) const { return list_env(l) + cfg.num_envs; }
     int64_t *actions() const { return reinterpret_cast<int64_t *>(static_cast<char *>(b.workspace) + ws.actions); }
+    uint32_t *obs_order() const { return reinterpret_cast<uint32_t *>(static_cast<char *>(b.workspace) + ws.obs_order); }
     uint32_t *hi_scratch() const { return reinterpret_cast<uint32_t *>(static_cast<char *>(b.workspace) + ws.hi); }
 };
 
@@ -147,6 +157,7 @@ ffmp::StepArgs step_args(const ffmp_handle *h) {
     a.term_rel_goal = b.term_rel_goal; a.term_velocity = b.term_velocity; a.fin_return = b.fin_return;
     a.done = b.done; a.flags = b.flags; a.fin_length = b.fin_length;
     a.error_word = h->error_word();
+    a.obs_order = h->obs_order();
     return a;
 }
 
@@ -171,15 +182,16 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
     a.regen_env = h->list_env(l); a.regen_episode = h->list_episode(l); a.regen_count = h->list_count(l);
     CK(ffmp::launch_step(a, st));
     CK(cudaEventRecord(h->ev_step[l], st));
-    CK(cudaStreamWaitEvent(h->side, h->ev_step[l], 0));
+    CK(cudaStreamWaitEvent(h->side[l], h->ev_step[l], 0));
     ffmp::ScenarioArgs sa = scenario_args(h);
     sa.env_idx = h->list_env(l); sa.episode = h->list_episode(l); sa.count_ptr = h->list_count(l);
-    CK(ffmp::launch_scenarios(sa, h->sc_grid, h->side));
+    CK(ffmp::launch_scenarios(sa, h->rg_grid, h->side[l]));
     ffmp::FlowArgs fa = flow_args(h);
     fa.env_idx = h->list_env(l); fa.episode = h->list_episode(l); fa.count_ptr = h->list_count(l);
     fa.ticket = h->list_ticket(l); fa.count_reset = h->list_count(l);
-    CK(ffmp::launch_flow_field(fa, h->ff_grid, h->side));
-    CK(cudaEventRecord(h->ev_regen[l], h->side));
+    fa.hi_scratch = h->hi_scratch() + (static_cast<size_t>(h->ff_grid) + static_cast<size_t>(l) * h->rg_grid) * ffmp::flow_field_scratch_words(h->cfg.grid);
+    CK(ffmp::launch_flow_field(fa, h->rg_grid, h->side[l]));
+    CK(cudaEventRecord(h->ev_regen[l], h->side[l]));
     h->regen_pending[l] = true;
     h->step_index += 1;
     return FFMP_OK;
@@ -221,10 +233,11 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
     h->ws = workspace_layout(cfg);
     h->nlist = cfg->slots - 1;
     std::memset(&h->b, 0, sizeof(h->b));
-    for (int i = 0; i < MAX_LISTS; ++i) { h->ev_step[i] = nullptr; h->ev_regen[i] = nullptr; h->regen_pending[i] = false; }
-    cudaError_t ce = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+    for (int i = 0; i < MAX_LISTS; ++i) { h->side[i] = nullptr; h->ev_step[i] = nullptr; h->ev_regen[i] = nullptr; h->regen_pending[i] = false; }
+    cudaError_t ce = cudaSuccess;
     for (int i = 0; i < h->nlist && ce == cudaSuccess; ++i) {
-        ce = cudaEventCreateWithFlags(&h->ev_step[i], cudaEventDisableTiming);
+        ce = cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_step[i], cudaEventDisableTiming);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_regen[i], cudaEventDisableTiming);
     }
     if (ce != cudaSuccess) {
@@ -234,6 +247,7 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
     const int maxg = ffmp::flow_field_max_grid(cfg->grid);
     h->ff_grid = cfg->num_envs < maxg ? cfg->num_envs : maxg;
     h->sc_grid = cfg->num_envs < 148 * 8 ? cfg->num_envs : 148 * 8;
+    h->rg_grid = cfg->num_envs < REGEN_GRID ? cfg->num_envs : REGEN_GRID;
     *out = h;
     return FFMP_OK;
 }
@@ -260,11 +274,11 @@ int ffmp_bind(ffmp_handle *h, const ffmp_buffers *bufs) {
 int ffmp_destroy(ffmp_handle *h) {
     if (!h) return FFMP_OK;
     DeviceGuard guard(h->cfg.device);
-    if (h->side) {
-        cudaStreamSynchronize(h->side);
-        cudaStreamDestroy(h->side);
-    }
     for (int i = 0; i < MAX_LISTS; ++i) {
+        if (h->side[i]) {
+            cudaStreamSynchronize(h->side[i]);
+            cudaStreamDestroy(h->side[i]);
+        }
         if (h->ev_step[i]) cudaEventDestroy(h->ev_step[i]);
         if (h->ev_regen[i]) cudaEventDestroy(h->ev_regen[i]);
     }
@@ -423,7 +437,7 @@ int ffmp_op_rewarder(int32_t device, int32_t n, int32_t W, const int32_t *local_
     return run_rewarder(device, a, stream);
 }
 
-int ffmp_op_rewarder2(int32_t device, int32_t n, int32_t scan_len, const float *scan_dev, const float *rel_goal_dev,
+int ffmp_op_rewarder2(int32_t device, int32_t n, int32_t scan_len, const double *scan_dev, const float *rel_goal_dev,
                       const uint8_t *is_first_dev, float *d_first_dev, float *reward_dev, uint8_t *done_dev,
                       uint8_t *flags_dev, void *stream) {
     if (scan_len < 0 || !scan_dev) return fail(FFMP_ERR_ARG, "bad argument");

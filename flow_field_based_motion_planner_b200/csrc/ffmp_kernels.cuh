@@ -53,13 +53,14 @@ struct StepArgs {
     uint8_t *done, *flags;
     int32_t *fin_length;
     uint32_t *regen_env, *regen_episode, *regen_count;  // regeneration request list
+    uint32_t *obs_order;        // [N][8] crop orders, dynamics_kernel -> observe_kernel
     uint32_t *error_word;
 };
 
 struct RewarderArgs {
     int n, W;
     const int32_t *local_map;   // map-based collision (ffmp.py:85-105) or null
-    const float *scan;          // LiDAR ranges f32[n][scan_len], NaN = None (ffmp.py:108-117) or null
+    const double *scan;         // LiDAR ranges f64[n][scan_len], NaN = None (ffmp.py:108-117) or null
     int scan_len;
     const uint8_t *given_flags; // explicit bit0 collision / bit1 goal (ffmp.py:130 signature) or null
     const float *rel_goal;

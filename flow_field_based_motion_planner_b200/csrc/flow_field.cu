@@ -236,103 +236,97 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
         }
         const uint32_t Lmax = L - 1;                       // deepest level that reached a cell
         const int kmax = 32 - __clz(Lmax);                  // number of significant cost bits
+        // visited (= reached free) and free masks go to scratch planes 14/15 so that the remaining
+        // phases can be ROLLED loops over (row, word) reading memory: keeps the code inside the I-cache
+        constexpr int PVIS = 14, PFREE = 15;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            uint32_t v[WPR];
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) v[w] = FR[r][w] & ~A[r][w];
+            Row<WPR>::st(&hi[pidx(PVIS - NPL, r, lane)], v);
+            Row<WPR>::st(&hi[pidx(PFREE - NPL, r, lane)], FR[r]);
+        }
         __syncwarp();
 
         // ---- 5. Gray -> binary, in place ---------------------------------------------------------
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < RPL; ++r) {
             uint32_t acc[WPR];
 #pragma unroll
             for (int w = 0; w < WPR; ++w) acc[w] = 0;
-            for (int k = kmax - 1; k >= NPL; --k) {
+#pragma unroll 1
+            for (int k = kmax - 1; k >= 0; --k) {
+                uint32_t v[WPR];
+                uint32_t *p = k < NPL ? &pl[pidx(k, r, lane)] : &hi[pidx(k - NPL, r, lane)];
+                Row<WPR>::ld(p, v);
 #pragma unroll
-                for (int w = 0; w < WPR; ++w) {
-                    uint32_t *p = &hi[pidx(k - NPL, r, lane) + w];
-                    acc[w] ^= *p;
-                    *p = acc[w];
-                }
-            }
-#pragma unroll
-            for (int k = NPL - 1; k >= 0; --k) {
-                if (k < kmax) {
-                    uint32_t v[WPR];
-                    uint32_t *p = &pl[pidx(k, r, lane)];
-                    Row<WPR>::ld(p, v);
-#pragma unroll
-                    for (int w = 0; w < WPR; ++w) { acc[w] ^= v[w]; v[w] = acc[w]; }
-                    Row<WPR>::st(p, v);
-                }
+                for (int w = 0; w < WPR; ++w) { acc[w] ^= v[w]; v[w] = acc[w]; }
+                Row<WPR>::st(p, v);
             }
         }
-
-        // visited = reached free cells
-        uint32_t V[RPL][WPR];
-#pragma unroll
-        for (int r = 0; r < RPL; ++r)
-#pragma unroll
-            for (int w = 0; w < WPR; ++w) V[r][w] = FR[r][w] & ~A[r][w];
+        __syncwarp();
 
         // ---- 6. expand the integration field to int32 and store ---------------------------------
         if (a.cost) {
             int32_t *cost = a.cost + plane * cells;
-#pragma unroll
-            for (int r = 0; r < RPL; ++r) {
+            const int klo = kmax < NPL ? kmax : NPL;
+#pragma unroll 1
+            for (int rw = 0; rw < RPL * WPR; ++rw) {
+                const int r = rw / WPR, w = rw - r * WPR;
                 const int R = lane * RPL + r;
-                if (R >= G) continue;
+                if (R >= G || 32 * w >= G) continue;
+                uint32_t lo[8], hb[8];
 #pragma unroll
-                for (int w = 0; w < WPR; ++w) {
-                    if (32 * w >= G) continue;
-                    uint32_t lo[8], hb[8];
+                for (int n = 0; n < 8; ++n) { lo[n] = 0; hb[n] = 0; }
+#pragma unroll 1
+                for (int k = 0; k < klo; ++k) {
+                    const uint32_t word = pl[pidx(k, r, lane) + w];
 #pragma unroll
-                    for (int n = 0; n < 8; ++n) { lo[n] = 0; hb[n] = 0; }
+                    for (int n = 0; n < 8; ++n) lo[n] += spread4(word, n) << k;
+                }
+#pragma unroll 1
+                for (int k = NPL; k < kmax; ++k) {
+                    const uint32_t word = hi[pidx(k - NPL, r, lane) + w];
 #pragma unroll
-                    for (int k = 0; k < NPL; ++k) {
-                        if (k < kmax) {
-                            const uint32_t word = pl[pidx(k, r, lane) + w];
+                    for (int n = 0; n < 8; ++n) hb[n] += spread4(word, n) << (k - NPL);
+                }
+                const uint32_t vis = hi[pidx(PVIS - NPL, r, lane) + w];
+                int32_t *dst = cost + static_cast<size_t>(R) * G + 32 * w;
 #pragma unroll
-                            for (int n = 0; n < 8; ++n) lo[n] += spread4(word, n) << k;
-                        }
-                    }
-                    for (int k = NPL; k < kmax; ++k) {
-                        const uint32_t word = hi[pidx(k - NPL, r, lane) + w];
-#pragma unroll
-                        for (int n = 0; n < 8; ++n) hb[n] += spread4(word, n) << (k - NPL);
-                    }
-                    const uint32_t vis = V[r][w];
-#pragma unroll
-                    for (int n = 0; n < 8; ++n) {
-                        if (32 * w + 4 * n >= G) continue;
-                        int4 c;
-                        c.x = (vis >> (4 * n + 0)) & 1 ? static_cast<int>((lo[n] & 0xFF) | ((hb[n] & 0xFF) << 8)) : COST_INF;
-                        c.y = (vis >> (4 * n + 1)) & 1 ? static_cast<int>(((lo[n] >> 8) & 0xFF) | (((hb[n] >> 8) & 0xFF) << 8)) : COST_INF;
-                        c.z = (vis >> (4 * n + 2)) & 1 ? static_cast<int>(((lo[n] >> 16) & 0xFF) | (((hb[n] >> 16) & 0xFF) << 8)) : COST_INF;
-                        c.w = (vis >> (4 * n + 3)) & 1 ? static_cast<int>((lo[n] >> 24) | ((hb[n] >> 24) << 8)) : COST_INF;
-                        *reinterpret_cast<int4 *>(cost + static_cast<size_t>(R) * G + 32 * w + 4 * n) = c;
-                    }
+                for (int n = 0; n < 8; ++n) {
+                    if (32 * w + 4 * n >= G) continue;
+                    int4 c;
+                    c.x = (vis >> (4 * n + 0)) & 1 ? static_cast<int>((lo[n] & 0xFF) | ((hb[n] & 0xFF) << 8)) : COST_INF;
+                    c.y = (vis >> (4 * n + 1)) & 1 ? static_cast<int>(((lo[n] >> 8) & 0xFF) | (((hb[n] >> 8) & 0xFF) << 8)) : COST_INF;
+                    c.z = (vis >> (4 * n + 2)) & 1 ? static_cast<int>(((lo[n] >> 16) & 0xFF) | (((hb[n] >> 16) & 0xFF) << 8)) : COST_INF;
+                    c.w = (vis >> (4 * n + 3)) & 1 ? static_cast<int>((lo[n] >> 24) | ((hb[n] >> 24) << 8)) : COST_INF;
+                    *reinterpret_cast<int4 *>(dst + 4 * n) = c;
                 }
             }
         }
         __syncwarp();
 
-        // ---- 7. flow direction, bit-parallel, and the flow image ---------------------------------
-        // planes 3 and 4 are no longer needed: reuse them for the visited / free masks so that the
-        // rows of the neighbouring lanes can be read back.
+        // ---- 7. flow direction, bit-parallel -----------------------------------------------------
+        // Resident planes 3..7 are free now: 3 = visited, 4 = free (neighbour rows are read back from
+        // other lanes), 5/6/7 + plane 0 (own row only) receive the 4 direction-code bit-planes.
         constexpr int PV = 3, PF = 4;
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < RPL; ++r) {
-            Row<WPR>::st(&pl[pidx(PV, r, lane)], V[r]);
-            Row<WPR>::st(&pl[pidx(PF, r, lane)], FR[r]);
+            uint32_t v[WPR];
+            Row<WPR>::ld(&hi[pidx(PVIS - NPL, r, lane)], v);
+            Row<WPR>::st(&pl[pidx(PV, r, lane)], v);
+            Row<WPR>::ld(&hi[pidx(PFREE - NPL, r, lane)], v);
+            Row<WPR>::st(&pl[pidx(PF, r, lane)], v);
         }
         __syncwarp();
-        uint8_t *flow = a.flow + plane * cells;
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < RPL; ++r) {
-            const int R = lane * RPL + r;
             // rows R-1 (west, "u") and R+1 (east, "d")
             const int lu = r == 0 ? lane - 1 : lane, ru = r == 0 ? RPL - 1 : r - 1;
             const int ld = r == RPL - 1 ? lane + 1 : lane, rd = r == RPL - 1 ? 0 : r + 1;
             uint32_t b0[WPR], b1c[WPR], b2c[WPR], b1u[WPR], b2u[WPR], b1d[WPR], b2d[WPR];
-            uint32_t Vu[WPR], Vd[WPR], Fu[WPR], Fd[WPR];
+            uint32_t Vc[WPR], Vu[WPR], Vd[WPR], Fc[WPR], Fu[WPR], Fd[WPR];
 #pragma unroll
             for (int w = 0; w < WPR; ++w) {
                 b0[w] = b1c[w] = b2c[w] = b1u[w] = b2u[w] = b1d[w] = b2d[w] = 0;
@@ -341,6 +335,8 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
             if (kmax > 0) Row<WPR>::ld(&pl[pidx(0, r, lane)], b0);
             if (kmax > 1) Row<WPR>::ld(&pl[pidx(1, r, lane)], b1c);
             if (kmax > 2) Row<WPR>::ld(&pl[pidx(2, r, lane)], b2c);
+            Row<WPR>::ld(&pl[pidx(PV, r, lane)], Vc);
+            Row<WPR>::ld(&pl[pidx(PF, r, lane)], Fc);
             if (lu >= 0) {
                 if (kmax > 1) Row<WPR>::ld(&pl[pidx(1, ru, lu)], b1u);
                 if (kmax > 2) Row<WPR>::ld(&pl[pidx(2, ru, lu)], b2u);
@@ -353,20 +349,19 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
                 Row<WPR>::ld(&pl[pidx(PV, rd, ld)], Vd);
                 Row<WPR>::ld(&pl[pidx(PF, rd, ld)], Fd);
             }
-            if (R >= G) continue;
+            uint32_t d0[WPR], d1[WPR], d2[WPR], d3[WPR];
 #pragma unroll
             for (int w = 0; w < WPR; ++w) {
-                if (32 * w >= G) continue;
-                const uint32_t own = V[r][w];
+                const uint32_t own = Vc[w];
                 const uint32_t t = b1c[w] ^ ~b0[w];   // bit 1 of (cost-1)
                 const uint32_t u = b2c[w] ^ ~b1c[w];  // bit 2 of (cost-2)
                 // orthogonal neighbours one level lower (codes 0 E, 2 N, 4 W, 6 S)
                 const uint32_t lE = own & Vd[w] & ~(b1d[w] ^ t);
                 const uint32_t lW = own & Vu[w] & ~(b1u[w] ^ t);
-                const uint32_t lN = own & shr1<WPR>(V[r], w) & ~(shr1<WPR>(b1c, w) ^ t);
-                const uint32_t lS = own & shl1<WPR>(V[r], w) & ~(shl1<WPR>(b1c, w) ^ t);
+                const uint32_t lN = own & shr1<WPR>(Vc, w) & ~(shr1<WPR>(b1c, w) ^ t);
+                const uint32_t lS = own & shl1<WPR>(Vc, w) & ~(shl1<WPR>(b1c, w) ^ t);
                 // admissible diagonals two levels lower (codes 1 NE, 3 NW, 5 SW, 7 SE)
-                const uint32_t fE = Fd[w], fW = Fu[w], fN = shr1<WPR>(FR[r], w), fS = shl1<WPR>(FR[r], w);
+                const uint32_t fE = Fd[w], fW = Fu[w], fN = shr1<WPR>(Fc, w), fS = shl1<WPR>(Fc, w);
                 const uint32_t lNE = own & shr1<WPR>(Fd, w) & fE & fN & (shr1<WPR>(b1d, w) ^ b1c[w]) & ~(shr1<WPR>(b2d, w) ^ u);
                 const uint32_t lNW = own & shr1<WPR>(Fu, w) & fW & fN & (shr1<WPR>(b1u, w) ^ b1c[w]) & ~(shr1<WPR>(b2u, w) ^ u);
                 const uint32_t lSW = own & shl1<WPR>(Fu, w) & fW & fS & (shl1<WPR>(b1u, w) ^ b1c[w]) & ~(shl1<WPR>(b2u, w) ^ u);
@@ -376,19 +371,36 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
                 const uint32_t m1 = (anyD & lNW) | (~anyD & lN);
                 const uint32_t m2 = (anyD & lSW) | (~anyD & lW);
                 const uint32_t m3 = (anyD & lSE) | (~anyD & lS);
-                const uint32_t has = m0 | m1 | m2 | m3;
-                const uint32_t d0 = anyD;
-                const uint32_t d1 = ~m0 & (m1 | (~m2 & m3));
-                const uint32_t d2 = ~m0 & ~m1 & (m2 | m3);
-                const uint32_t d3 = ~has;
-                const uint32_t occ = ~FR[r][w];
+                d0[w] = anyD;
+                d1[w] = ~m0 & (m1 | (~m2 & m3));
+                d2[w] = ~m0 & ~m1 & (m2 | m3);
+                d3[w] = ~(m0 | m1 | m2 | m3);
+            }
+            // b0 of this row is not read by any other lane: the row can be overwritten right away
+            Row<WPR>::st(&pl[pidx(0, r, lane)], d0);
+            Row<WPR>::st(&pl[pidx(5, r, lane)], d1);
+            Row<WPR>::st(&pl[pidx(6, r, lane)], d2);
+            Row<WPR>::st(&pl[pidx(7, r, lane)], d3);
+        }
+        __syncwarp();
+
+        // ---- 8. expand the flow image (255 occupied, else dir*28) and store ----------------------
+        uint8_t *flow = a.flow + plane * cells;
+#pragma unroll 1
+        for (int rw = 0; rw < RPL * WPR; ++rw) {
+            const int r = rw / WPR, w = rw - r * WPR;
+            const int R = lane * RPL + r;
+            if (R >= G || 32 * w >= G) continue;
+            const uint32_t d0 = pl[pidx(0, r, lane) + w], d1 = pl[pidx(5, r, lane) + w];
+            const uint32_t d2 = pl[pidx(6, r, lane) + w], d3 = pl[pidx(7, r, lane) + w];
+            const uint32_t occ = ~pl[pidx(PF, r, lane) + w];
+            uint8_t *dst = flow + static_cast<size_t>(R) * G + 32 * w;
 #pragma unroll
-                for (int n = 0; n < 8; ++n) {
-                    if (32 * w + 4 * n >= G) continue;
-                    uint32_t v = spread4(d0, n) * 28u + spread4(d1, n) * 56u + spread4(d2, n) * 112u + spread4(d3, n) * 224u;
-                    v |= spread4(occ, n) * 255u;
-                    *reinterpret_cast<uint32_t *>(flow + static_cast<size_t>(R) * G + 32 * w + 4 * n) = v;
-                }
+            for (int n = 0; n < 8; ++n) {
+                if (32 * w + 4 * n >= G) continue;
+                uint32_t v = spread4(d0, n) * 28u + spread4(d1, n) * 56u + spread4(d2, n) * 112u + spread4(d3, n) * 224u;
+                v |= spread4(occ, n) * 255u;
+                *reinterpret_cast<uint32_t *>(dst + 4 * n) = v;
             }
         }
         __syncwarp();

@@ -1,12 +1,15 @@
-// step.cu — SPEC.md §7/§8: the fused per-step kernel of the batched FFMP environment.
+// step.cu — SPEC.md §7/§8: the per-step kernels of the batched FFMP environment.
 //
-// One CTA (4 warps) per environment.  Warp 0 runs the scalar part — fp32 unicycle integration
-// (SPEC K), relative goal / velocity (train.py:174-188), the 21-cell footprint collision test on the
-// global flow image (ffmp.py:85-105), goal test, reward, done, truncation (ffmp.py:120-164,
-// train.py:607-608), auto-reset onto the next pre-generated scenario slot — and broadcasts the crop
-// origin through shared memory; all four warps then copy the ego-centred W x W window of the flow
-// image into the observation frame ring with coalesced 32-bit stores (byte-realigned with a funnel
-// shift).  HBM-bound: W^2 read + W^2 written per env-step (+ one more frame on ring wrap / reset).
+// dynamics_kernel — ONE THREAD PER ENVIRONMENT: fp32 unicycle integration (SPEC K), relative goal /
+//   velocity (train.py:174-188), the 21-cell footprint collision test on the global flow image
+//   (ffmp.py:85-105), goal test, reward, done, truncation (ffmp.py:120-164, train.py:607-608), the
+//   auto-reset onto the next pre-generated scenario slot and the regeneration request; it leaves a
+//   32-byte crop order per env.  Latency-bound (three dependent memory round trips), ~100 B/env.
+// observe_kernel — one CTA per environment: copies the ego-centred W x W window of the flow image into
+//   the observation frame ring with coalesced 32-bit stores (byte-realigned with a funnel shift, eight
+//   rows of loads in flight per thread).  HBM-bound: W^2 read + W^2 written per env-step (+ one more
+//   frame on ring wrap / reset).  Launched with programmatic dependent launch so that its CTAs are
+//   resident and waiting (griddepcontrol.wait) when dynamics_kernel retires.
 #include "ffmp_kernels.cuh"
 
 namespace ffmp {
@@ -16,179 +19,221 @@ namespace {
 __constant__ int8_t FOOT_DI[21] = {-2, -2, -2, -1, -1, -1, -1, -1, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2};
 __constant__ int8_t FOOT_DJ[21] = {-1, 0, 1, -2, -1, 0, 1, 2, -2, -1, 0, 1, 2, -2, -1, 0, 1, 2, -1, 0, 1};
 
-struct Bcast {
-    int active;          // this env writes frames in this call
-    int two;             // also write the older frame
-    int ci, cj;          // crop centre of the newest frame
-    int pi, pj;          // crop centre of the older frame
-    unsigned long long plane;  // scenario plane index of the flow image
+// crop order written by dynamics_kernel for observe_kernel (8 words per env)
+enum { OB_CI = 0, OB_CJ, OB_PI, OB_PJ, OB_PLANE, OB_FLAGS, OB_WORDS = 8 };   // flags: bit0 active, bit1 two frames
+
+// Per-lane plan for one 4-byte output word of a crop row.  The byte misalignment m of the window
+// against the 4-byte aligned source row is the same for every word of a frame; out-of-grid columns
+// are forced to 255 through `ormask`, and the two aligned source words are clamped into the row so
+// that every load is in bounds (G % 4 == 0: an aligned word is either fully in or fully out).
+struct ColPlan {
+    int off_lo, off_hi;   // byte offsets of the aligned source words inside a grid row
+    uint32_t ormask;      // 0xFF in every byte whose column is out of the grid
+    int shift;            // 8 * m
 };
 
-__device__ __forceinline__ uint32_t crop_word(const uint8_t *__restrict__ img, int G, int i, int j0) {
-    if (static_cast<unsigned>(i) >= static_cast<unsigned>(G)) return 0xFFFFFFFFu;
-    const uint8_t *row = img + static_cast<size_t>(i) * G;
-    if (j0 >= 0 && j0 + 3 < G) {
-        const int m = j0 & 3;
-        const uint32_t *wp = reinterpret_cast<const uint32_t *>(row + (j0 - m));
-        const uint32_t lo = __ldg(wp);
-        const uint32_t hi = m ? __ldg(wp + 1) : 0u;
-        return __funnelshift_r(lo, hi, 8 * m);
-    }
-    uint32_t v = 0;
+__device__ __forceinline__ ColPlan make_plan(int G, int j0) {
+    ColPlan p;
+    const int a = j0 & ~3;                 // aligned start (floor to a multiple of 4, also for negatives)
+    const int m = j0 - a;
+    p.shift = 8 * m;
+    const int last = G - 4;
+    p.off_lo = min(max(a, 0), last);
+    p.off_hi = min(max(a + 4, 0), last);
+    uint32_t om = 0;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const int j = j0 + c;
-        const uint32_t b = static_cast<unsigned>(j) < static_cast<unsigned>(G) ? __ldg(row + j) : 255u;
-        v |= b << (8 * c);
-    }
-    return v;
+    for (int c = 0; c < 4; ++c)
+        if (static_cast<unsigned>(j0 + c) >= static_cast<unsigned>(G)) om |= 0xFFu << (8 * c);
+    p.ormask = om;
+    return p;
 }
 
-__global__ void __launch_bounds__(128) step_kernel(StepArgs a) {
-    __shared__ Bcast bc;
+__device__ __forceinline__ uint32_t crop_word(const uint8_t *__restrict__ img, int G, int i, const ColPlan &p) {
+    if (static_cast<unsigned>(i) >= static_cast<unsigned>(G)) return 0xFFFFFFFFu;
+    const uint8_t *row = img + static_cast<size_t>(i) * G;
+    const uint32_t lo = __ldg(reinterpret_cast<const uint32_t *>(row + p.off_lo));
+    const uint32_t hi = __ldg(reinterpret_cast<const uint32_t *>(row + p.off_hi));
+    return __funnelshift_r(lo, hi, p.shift) | p.ormask;
+}
+
+__global__ void __launch_bounds__(128) dynamics_kernel(StepArgs a) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.N) return;
+    const int G = a.G;
+    const size_t cells = static_cast<size_t>(G) * G;
+    uint32_t *st = a.state + static_cast<size_t>(e) * ST_WORDS;
+    const uint4 s0 = *reinterpret_cast<const uint4 *>(st);        // x y yaw gx
+    const uint4 s1 = *reinterpret_cast<const uint4 *>(st + 4);    // gy d_first return steps
+    float x = __uint_as_float(s0.x), y = __uint_as_float(s0.y), yaw = __uint_as_float(s0.z);
+    const float gx = __uint_as_float(s0.w), gy = __uint_as_float(s1.x);
+    const float d_first = __uint_as_float(s1.y);
+    float ep_return = __uint_as_float(s1.z);
+    int steps = static_cast<int>(s1.w);
+    uint32_t episode = st[ST_EPISODE];
+    bool begin = false, active = true;
+    int ci = 0, cj = 0, pi = 0, pj = 0;
+
+    if (a.mode == 0) {
+        long long act = a.actions[e];
+        if (act < 0 || act >= 28) {
+            act = 3;
+            atomicOr(a.error_word, 1u);
+        }
+        float v, w, s, c;
+        action_lookup(static_cast<int>(act), v, w);
+        sincos_spec(yaw, s, c);
+        const float nx = fadd(x, fmul(fmul(v, c), a.dt));
+        const float ny = fadd(y, fmul(fmul(v, s), a.dt));
+        const float nyaw = pi_to_pi(fadd(yaw, fmul(w, a.dt)));
+        ci = robot_cell(nx);
+        cj = robot_cell(ny);
+        // footprint: 21 independent byte loads in flight
+        const uint8_t *img = a.flow + (static_cast<size_t>(episode % a.S) * a.N + e) * cells;
+        bool col = false;
+        if (ci >= 2 && cj >= 2 && ci < G - 2 && cj < G - 2) {
+            uint32_t hit = 0;
+#pragma unroll
+            for (int k = 0; k < 21; ++k)
+                hit |= __ldg(img + static_cast<size_t>(ci + FOOT_DI[k]) * G + (cj + FOOT_DJ[k])) == 255 ? 1u : 0u;
+            col = hit != 0;
+        } else {
+            col = true;   // some footprint cell is out of the grid
+        }
+        const float dx = fsub(gx, nx), dy = fsub(gy, ny);
+        const float d = dist_spec(dx, dy);
+        const float bearing = pi_to_pi(fsub(atan2_spec(dy, dx), nyaw));
+        const float vl = dist_spec(fsub(nx, x), fsub(ny, y));
+        const float va = pi_to_pi(fsub(nyaw, yaw));
+        const bool goal = d < 0.5f;
+        const float r = fadd(fadd(goal ? 1.0f : fmul(0.05f, fsub(d_first, d)), col ? -1.0f : 0.0f), -0.05f);
+        steps += 1;
+        const bool trunc = steps == a.max_steps;
+        const bool done = col || goal || trunc;
+        ep_return = fadd(ep_return, r);
+        a.reward[e] = r;
+        a.done[e] = done ? 1 : 0;
+        a.flags[e] = static_cast<uint8_t>((col ? 1 : 0) | (goal ? 2 : 0) | (trunc ? 4 : 0));
+        *reinterpret_cast<float2 *>(a.term_rel_goal + 2 * e) = make_float2(d, bearing);
+        *reinterpret_cast<float2 *>(a.term_velocity + 2 * e) = make_float2(vl, va);
+        if (done) {
+            a.fin_return[e] = ep_return;
+            a.fin_length[e] = steps;
+            begin = true;
+        } else {
+            pi = robot_cell(x);
+            pj = robot_cell(y);
+            st[ST_X] = __float_as_uint(nx); st[ST_Y] = __float_as_uint(ny); st[ST_YAW] = __float_as_uint(nyaw);
+            st[ST_RETURN] = __float_as_uint(ep_return);
+            st[ST_STEPS] = static_cast<uint32_t>(steps);
+            *reinterpret_cast<float2 *>(a.rel_goal + 2 * e) = make_float2(d, bearing);
+            *reinterpret_cast<float2 *>(a.velocity + 2 * e) = make_float2(vl, va);
+        }
+    } else if (a.mode == 1) {
+        begin = a.mask[e] != 0;
+        active = begin;
+    } else {
+        begin = true;
+    }
+
+    if (begin) {
+        if (a.mode != 2) {
+            episode += 1;
+            // the slot of the finished episode is refilled with episode + S - 1
+            const uint32_t idx = atomicAdd(a.regen_count, 1u);
+            a.regen_env[idx] = static_cast<uint32_t>(e);
+            a.regen_episode[idx] = episode + static_cast<uint32_t>(a.S) - 1u;
+        }
+        const uint32_t *rec = a.scen + (static_cast<size_t>(episode % a.S) * a.N + e) * SC_WORDS;
+        const uint4 r0 = *reinterpret_cast<const uint4 *>(rec);
+        x = __uint_as_float(r0.x); y = __uint_as_float(r0.y); yaw = __uint_as_float(r0.z);
+        const float ngx = __uint_as_float(r0.w), ngy = __uint_as_float(rec[SC_GY]);
+        const float dx = fsub(ngx, x), dy = fsub(ngy, y);
+        const float d = dist_spec(dx, dy);
+        const float bearing = pi_to_pi(fsub(atan2_spec(dy, dx), yaw));
+        ci = pi = robot_cell(x);
+        cj = pj = robot_cell(y);
+        *reinterpret_cast<uint4 *>(st) = make_uint4(__float_as_uint(x), __float_as_uint(y), __float_as_uint(yaw), __float_as_uint(ngx));
+        *reinterpret_cast<uint4 *>(st + 4) = make_uint4(__float_as_uint(ngy), __float_as_uint(d), __float_as_uint(0.0f), 0u);
+        st[ST_EPISODE] = episode;
+        *reinterpret_cast<float2 *>(a.rel_goal + 2 * e) = make_float2(d, bearing);
+        *reinterpret_cast<float2 *>(a.velocity + 2 * e) = make_float2(0.0f, 0.0f);
+        if (a.mode == 2) { a.reward[e] = 0.0f; a.done[e] = 0; a.flags[e] = 0; }
+    }
+    uint32_t *ob = a.obs_order + static_cast<size_t>(e) * OB_WORDS;
+    *reinterpret_cast<uint4 *>(ob) = make_uint4(static_cast<uint32_t>(ci), static_cast<uint32_t>(cj),
+                                               static_cast<uint32_t>(pi), static_cast<uint32_t>(pj));
+    *reinterpret_cast<uint2 *>(ob + 4) = make_uint2((episode % a.S) * static_cast<uint32_t>(a.N) + static_cast<uint32_t>(e),
+                                                   (active ? 1u : 0u) | ((begin || a.write_older) ? 2u : 0u));
+}
+
+constexpr int ROWS_IN_FLIGHT = 8;
+
+// one frame: `nrow` rows per lane (row = row0 + k*stride), ROWS_IN_FLIGHT rows of loads issued before the stores
+__device__ __forceinline__ void crop_rows(const uint8_t *__restrict__ img, int G, int W, int wpr, int i0, int row0,
+                                          int stride, int wl, const ColPlan &p, uint32_t *__restrict__ dst,
+                                          uint32_t *__restrict__ dst2) {
+    for (int base = row0; base < W; base += ROWS_IN_FLIGHT * stride) {
+        uint32_t lo[ROWS_IN_FLIGHT], hi[ROWS_IN_FLIGHT];
+#pragma unroll
+        for (int k = 0; k < ROWS_IN_FLIGHT; ++k) {
+            const int row = base + k * stride, i = i0 + row;
+            lo[k] = 0xFFFFFFFFu; hi[k] = 0xFFFFFFFFu;
+            if (row < W && static_cast<unsigned>(i) < static_cast<unsigned>(G)) {
+                const uint8_t *src = img + static_cast<size_t>(i) * G;
+                lo[k] = __ldg(reinterpret_cast<const uint32_t *>(src + p.off_lo));
+                hi[k] = __ldg(reinterpret_cast<const uint32_t *>(src + p.off_hi));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < ROWS_IN_FLIGHT; ++k) {
+            const int row = base + k * stride;
+            if (row < W) {
+                const uint32_t v = __funnelshift_r(lo[k], hi[k], p.shift) | p.ormask;
+                __stcs(dst + row * wpr + wl, v);                 // streaming store: frames are write-once
+                if (dst2) __stcs(dst2 + row * wpr + wl, v);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) observe_kernel(StepArgs a) {
     const int e = blockIdx.x;
     const int tid = threadIdx.x;
     const int G = a.G, W = a.W;
-    const size_t cells = static_cast<size_t>(G) * G;
-
-    if (tid < 32) {
-        const int lane = tid;
-        uint32_t *st = a.state + static_cast<size_t>(e) * ST_WORDS;
-        float x = __uint_as_float(st[ST_X]), y = __uint_as_float(st[ST_Y]), yaw = __uint_as_float(st[ST_YAW]);
-        const float gx = __uint_as_float(st[ST_GX]), gy = __uint_as_float(st[ST_GY]);
-        const float d_first = __uint_as_float(st[ST_DFIRST]);
-        float ep_return = __uint_as_float(st[ST_RETURN]);
-        int steps = static_cast<int>(st[ST_STEPS]);
-        uint32_t episode = st[ST_EPISODE];
-        bool begin = false, active = true;
-        int ci = 0, cj = 0, pi = 0, pj = 0;
-
-        if (a.mode == 0) {
-            long long act = a.actions[e];
-            if (act < 0 || act >= 28) {
-                act = 3;
-                if (lane == 0) atomicOr(a.error_word, 1u);
-            }
-            float v, w, s, c;
-            action_lookup(static_cast<int>(act), v, w);
-            sincos_spec(yaw, s, c);
-            const float nx = fadd(x, fmul(fmul(v, c), a.dt));
-            const float ny = fadd(y, fmul(fmul(v, s), a.dt));
-            const float nyaw = pi_to_pi(fadd(yaw, fmul(w, a.dt)));
-            const float dx = fsub(gx, nx), dy = fsub(gy, ny);
-            const float d = dist_spec(dx, dy);
-            const float bearing = pi_to_pi(fsub(atan2_spec(dy, dx), nyaw));
-            const float vl = dist_spec(fsub(nx, x), fsub(ny, y));
-            const float va = pi_to_pi(fsub(nyaw, yaw));
-            ci = robot_cell(nx);
-            cj = robot_cell(ny);
-            const uint8_t *img = a.flow + (static_cast<size_t>(episode % a.S) * a.N + e) * cells;
-            bool hit = false;
-            if (lane < 21) {
-                const int i = ci + FOOT_DI[lane], j = cj + FOOT_DJ[lane];
-                hit = static_cast<unsigned>(i) >= static_cast<unsigned>(G) || static_cast<unsigned>(j) >= static_cast<unsigned>(G);
-                if (!hit) hit = __ldg(img + static_cast<size_t>(i) * G + j) == 255;
-            }
-            const bool col = __ballot_sync(FULL, hit) != 0;
-            const bool goal = d < 0.5f;
-            const float r = fadd(fadd(goal ? 1.0f : fmul(0.05f, fsub(d_first, d)), col ? -1.0f : 0.0f), -0.05f);
-            steps += 1;
-            const bool trunc = steps == a.max_steps;
-            const bool done = col || goal || trunc;
-            ep_return = fadd(ep_return, r);
-            if (lane == 0) {
-                a.reward[e] = r;
-                a.done[e] = done ? 1 : 0;
-                a.flags[e] = static_cast<uint8_t>((col ? 1 : 0) | (goal ? 2 : 0) | (trunc ? 4 : 0));
-                a.term_rel_goal[2 * e] = d; a.term_rel_goal[2 * e + 1] = bearing;
-                a.term_velocity[2 * e] = vl; a.term_velocity[2 * e + 1] = va;
-            }
-            if (done) {
-                if (lane == 0) { a.fin_return[e] = ep_return; a.fin_length[e] = steps; }
-                begin = true;
-            } else {
-                pi = robot_cell(x); pj = robot_cell(y);
-                if (lane == 0) {
-                    st[ST_X] = __float_as_uint(nx); st[ST_Y] = __float_as_uint(ny); st[ST_YAW] = __float_as_uint(nyaw);
-                    st[ST_RETURN] = __float_as_uint(ep_return);
-                    st[ST_STEPS] = static_cast<uint32_t>(steps);
-                    a.rel_goal[2 * e] = d; a.rel_goal[2 * e + 1] = bearing;
-                    a.velocity[2 * e] = vl; a.velocity[2 * e + 1] = va;
-                }
-            }
-        } else if (a.mode == 1) {
-            begin = a.mask[e] != 0;
-            active = begin;
-        } else {
-            begin = true;
-        }
-
-        if (begin) {
-            if (a.mode != 2) {
-                episode += 1;
-                if (lane == 0) {
-                    // the slot of the finished episode is refilled with episode + S - 1
-                    const uint32_t idx = atomicAdd(a.regen_count, 1u);
-                    a.regen_env[idx] = static_cast<uint32_t>(e);
-                    a.regen_episode[idx] = episode + static_cast<uint32_t>(a.S) - 1u;
-                }
-            }
-            const uint32_t *rec = a.scen + (static_cast<size_t>(episode % a.S) * a.N + e) * SC_WORDS;
-            x = __uint_as_float(rec[SC_X0]); y = __uint_as_float(rec[SC_Y0]); yaw = __uint_as_float(rec[SC_YAW0]);
-            const float ngx = __uint_as_float(rec[SC_GX]), ngy = __uint_as_float(rec[SC_GY]);
-            const float dx = fsub(ngx, x), dy = fsub(ngy, y);
-            const float d = dist_spec(dx, dy);
-            const float bearing = pi_to_pi(fsub(atan2_spec(dy, dx), yaw));
-            ci = pi = robot_cell(x);
-            cj = pj = robot_cell(y);
-            if (lane == 0) {
-                st[ST_X] = __float_as_uint(x); st[ST_Y] = __float_as_uint(y); st[ST_YAW] = __float_as_uint(yaw);
-                st[ST_GX] = __float_as_uint(ngx); st[ST_GY] = __float_as_uint(ngy);
-                st[ST_DFIRST] = __float_as_uint(d);
-                st[ST_RETURN] = __float_as_uint(0.0f);
-                st[ST_STEPS] = 0u;
-                st[ST_EPISODE] = episode;
-                a.rel_goal[2 * e] = d; a.rel_goal[2 * e + 1] = bearing;
-                a.velocity[2 * e] = 0.0f; a.velocity[2 * e + 1] = 0.0f;
-                if (a.mode == 2) { a.reward[e] = 0.0f; a.done[e] = 0; a.flags[e] = 0; }
-            }
-        }
-        if (lane == 0) {
-            bc.active = active ? 1 : 0;
-            bc.two = (begin || a.write_older) ? 1 : 0;
-            bc.ci = ci; bc.cj = cj; bc.pi = pi; bc.pj = pj;
-            bc.plane = static_cast<unsigned long long>(episode % a.S) * a.N + e;
-        }
-    }
-    __syncthreads();
-    if (!bc.active) return;
-
-    // ---- observation: crop the flow image into the frame ring ------------------------------------
-    const uint8_t *img = a.flow + static_cast<size_t>(bc.plane) * cells;
-    const int wpr = W >> 2;
-    const int nwords = W * wpr;
+    const int wpr = W >> 2;                                  // output words per row
+    const int lane = tid & 31, warp = tid >> 5;
+    // everything above is independent of dynamics_kernel; its results are consumed below this point
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const uint32_t *ob = a.obs_order + static_cast<size_t>(e) * OB_WORDS;
+    const uint4 o0 = *reinterpret_cast<const uint4 *>(ob);
+    const uint2 o1 = *reinterpret_cast<const uint2 *>(ob + 4);
+    if (!(o1.y & 1u)) return;
+    const bool two = (o1.y & 2u) != 0;
+    const int ci = static_cast<int>(o0.x), cj = static_cast<int>(o0.y), pi = static_cast<int>(o0.z), pj = static_cast<int>(o0.w);
+    const uint8_t *img = a.flow + static_cast<size_t>(o1.x) * G * G;
     uint32_t *f_new = reinterpret_cast<uint32_t *>(a.frames + (static_cast<size_t>(e) * a.K + a.slot_new) * W * W);
-    uint32_t *f_old = reinterpret_cast<uint32_t *>(a.frames + (static_cast<size_t>(e) * a.K + a.slot_new - 1) * W * W);
-    const int i0 = bc.ci - (W >> 1), j00 = bc.cj - (W >> 1);
-    const bool two = bc.two != 0;
-    const bool same = bc.pi == bc.ci && bc.pj == bc.cj;
-    const int da = 128 / wpr, db = 128 - da * wpr;
-    int row = tid / wpr, bw = tid - row * wpr;
-    if (two && !same) {
-        const int p0 = bc.pi - (W >> 1), q0 = bc.pj - (W >> 1);
-        for (int q = tid; q < nwords; q += 128) {
-            f_new[q] = crop_word(img, G, i0 + row, j00 + 4 * bw);
-            f_old[q] = crop_word(img, G, p0 + row, q0 + 4 * bw);
-            row += da; bw += db;
-            if (bw >= wpr) { bw -= wpr; row += 1; }
+    uint32_t *f_old = f_new - (W * W >> 2);
+    const bool same = pi == ci && pj == cj;
+    const int i0 = ci - (W >> 1), j0 = cj - (W >> 1);
+    const int p0 = pi - (W >> 1), q0 = pj - (W >> 1);
+    if (wpr <= 32) {
+        const int rpi = 32 / wpr;                            // rows per warp iteration
+        const int sub = lane / wpr, wl = lane - sub * wpr;
+        if (sub >= rpi) return;
+        const ColPlan pn = make_plan(G, j0 + 4 * wl);
+        crop_rows(img, G, W, wpr, i0, warp * rpi + sub, 4 * rpi, wl, pn, f_new, (two && same) ? f_old : nullptr);
+        if (two && !same) {
+            const ColPlan po = make_plan(G, q0 + 4 * wl);
+            crop_rows(img, G, W, wpr, p0, warp * rpi + sub, 4 * rpi, wl, po, f_old, nullptr);
         }
     } else {
-        for (int q = tid; q < nwords; q += 128) {
-            const uint32_t v = crop_word(img, G, i0 + row, j00 + 4 * bw);
-            f_new[q] = v;
-            if (two) f_old[q] = v;
-            row += da; bw += db;
-            if (bw >= wpr) { bw -= wpr; row += 1; }
+        for (int wl = lane; wl < wpr; wl += 32) {
+            const ColPlan pn = make_plan(G, j0 + 4 * wl);
+            crop_rows(img, G, W, wpr, i0, warp, 4, wl, pn, f_new, (two && same) ? f_old : nullptr);
+            if (two && !same) {
+                const ColPlan po = make_plan(G, q0 + 4 * wl);
+                crop_rows(img, G, W, wpr, p0, warp, 4, wl, po, f_old, nullptr);
+            }
         }
     }
 }
@@ -207,9 +252,9 @@ __global__ void __launch_bounds__(128) rewarder_kernel(RewarderArgs a) {
         }
     } else if (a.scan) {
         for (int k = lane; k < a.scan_len; k += 32) {
-            const float r = a.scan[static_cast<size_t>(item) * a.scan_len + k];
-            // `if scan[i]: if scan[i] < 0.13` with None encoded as NaN; the threshold is the fp64 0.13
-            if (r == r && r != 0.0f && static_cast<double>(r) < 0.13) hit = true;
+            const double r = a.scan[static_cast<size_t>(item) * a.scan_len + k];
+            // `if scan[i]: if scan[i] < 0.13` on Python floats (fp64), None encoded as NaN
+            if (r == r && r != 0.0 && r < 0.13) hit = true;
         }
     }
     bool col = __ballot_sync(FULL, hit) != 0;
@@ -229,8 +274,21 @@ __global__ void __launch_bounds__(128) rewarder_kernel(RewarderArgs a) {
 
 cudaError_t launch_step(const StepArgs &a, cudaStream_t st) {
     if (a.N <= 0) return cudaSuccess;
-    step_kernel<<<a.N, 128, 0, st>>>(a);
-    return cudaGetLastError();
+    dynamics_kernel<<<(a.N + 127) / 128, 128, 0, st>>>(a);
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return ce;
+    // programmatic dependent launch: observe_kernel's CTAs become resident while dynamics_kernel drains
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(a.N));
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, observe_kernel, a);
 }
 
 cudaError_t launch_rewarder(const RewarderArgs &a, cudaStream_t st) {

@@ -39,7 +39,7 @@ class FFMP:
     @staticmethod
     def _scan(scan_data):
         vals = [float("nan") if r is None else float(r) for r in scan_data] or [float("nan")]
-        return torch.tensor([vals], dtype=torch.float32)
+        return torch.tensor([vals], dtype=torch.float64)
 
     def is_collision(self, local_map_info):                                   # ffmp.py:85-105
         scratch = self._d_first.clone()

@@ -50,6 +50,8 @@ def flow_field(occ, goal_cells, want_cost=True):
     goals = goal_cells.to(device=occ.device, dtype=torch.int32).contiguous()
     cost = torch.empty((n, G, G), dtype=torch.int32, device=occ.device) if want_cost else None
     flow = torch.empty((n, G, G), dtype=torch.uint8, device=occ.device)
+    if n == 0:
+        return cost, flow
     ws_bytes = L.ffmp_op_flow_field_workspace(n, G)
     if n > 0 and ws_bytes == 0:
         raise native.NativeError(f"flow_field: grid {G} is not supported by this build")
@@ -94,10 +96,10 @@ def rewarder(local_map, rel_goal, is_first, d_first):
 
 
 def rewarder2(scan, rel_goal, is_first, d_first):
-    """FFMP.rewarder2, batched: scan f32[n,B] LiDAR ranges (NaN = None) instead of a local map."""
+    """FFMP.rewarder2, batched: scan f64[n,B] LiDAR ranges (NaN = None) instead of a local map."""
     L = native.lib()
     dev = _dev_index(scan)
-    sc = scan.to(torch.float32).contiguous()
+    sc = scan.to(torch.float64).contiguous()
     n, B = sc.shape
     rg, first, reward, done, flags = _reward_common(n, sc.device, rel_goal, is_first, d_first)
     with torch.cuda.device(sc.device):

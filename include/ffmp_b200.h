@@ -159,9 +159,9 @@ int ffmp_op_rewarder(int32_t device, int32_t n, int32_t W, const int32_t *local_
                      const uint8_t *is_first_dev, float *d_first_dev, float *reward_dev, uint8_t *done_dev,
                      uint8_t *flags_dev, void *stream);
 
-/* Batched FFMP.rewarder2 (ffmp.py:179-188, the variant train.py:577 calls): scan f32[n][scan_len] LiDAR
+/* Batched FFMP.rewarder2 (ffmp.py:179-188, the variant train.py:577 calls): scan f64[n][scan_len] LiDAR
  * ranges, NaN = None; collision iff a non-zero range is < 0.13 (ffmp.py:108-117).                  */
-int ffmp_op_rewarder2(int32_t device, int32_t n, int32_t scan_len, const float *scan_dev, const float *rel_goal_dev,
+int ffmp_op_rewarder2(int32_t device, int32_t n, int32_t scan_len, const double *scan_dev, const float *rel_goal_dev,
                       const uint8_t *is_first_dev, float *d_first_dev, float *reward_dev, uint8_t *done_dev,
                       uint8_t *flags_dev, void *stream);
 
