@@ -48,14 +48,6 @@ __device__ __forceinline__ ColPlan make_plan(int G, int j0) {
     return p;
 }
 
-__device__ __forceinline__ uint32_t crop_word(const uint8_t *__restrict__ img, int G, int i, const ColPlan &p) {
-    if (static_cast<unsigned>(i) >= static_cast<unsigned>(G)) return 0xFFFFFFFFu;
-    const uint8_t *row = img + static_cast<size_t>(i) * G;
-    const uint32_t lo = __ldg(reinterpret_cast<const uint32_t *>(row + p.off_lo));
-    const uint32_t hi = __ldg(reinterpret_cast<const uint32_t *>(row + p.off_hi));
-    return __funnelshift_r(lo, hi, p.shift) | p.ormask;
-}
-
 __global__ void __launch_bounds__(128) dynamics_kernel(StepArgs a) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= a.N) return;
@@ -91,10 +83,14 @@ __global__ void __launch_bounds__(128) dynamics_kernel(StepArgs a) {
         const uint8_t *img = a.flow + (static_cast<size_t>(episode % a.S) * a.N + e) * cells;
         bool col = false;
         if (ci >= 2 && cj >= 2 && ci < G - 2 && cj < G - 2) {
+            // all 21 loads are issued before the first use (one memory round trip, not 21)
+            const uint8_t *centre = img + static_cast<size_t>(ci) * G + cj;
+            uint32_t cell[21];
+#pragma unroll
+            for (int k = 0; k < 21; ++k) cell[k] = __ldg(centre + (FOOT_DI[k] * G + FOOT_DJ[k]));
             uint32_t hit = 0;
 #pragma unroll
-            for (int k = 0; k < 21; ++k)
-                hit |= __ldg(img + static_cast<size_t>(ci + FOOT_DI[k]) * G + (cj + FOOT_DJ[k])) == 255 ? 1u : 0u;
+            for (int k = 0; k < 21; ++k) hit |= (cell[k] + 1u) >> 8;   // 255 -> 1, anything else -> 0
             col = hit != 0;
         } else {
             col = true;   // some footprint cell is out of the grid
@@ -168,31 +164,66 @@ __global__ void __launch_bounds__(128) dynamics_kernel(StepArgs a) {
 
 constexpr int ROWS_IN_FLIGHT = 8;
 
-// one frame: `nrow` rows per lane (row = row0 + k*stride), ROWS_IN_FLIGHT rows of loads issued before the stores
+__device__ __forceinline__ int ceil_div_pos(int a, int b) { return a <= 0 ? 0 : (a + b - 1) / b; }
+
+// One frame for one lane: rows row0, row0+stride, ... < W of output word column `wl`.
+// The lane's rows are split into [out-of-grid | in-grid | out-of-grid] so that the in-grid loop carries no
+// bounds checks; it indexes the image as 32-bit words (one IMAD.WIDE per access) and keeps
+// ROWS_IN_FLIGHT rows of loads in flight before the first store.
+template <bool TWO>
 __device__ __forceinline__ void crop_rows(const uint8_t *__restrict__ img, int G, int W, int wpr, int i0, int row0,
                                           int stride, int wl, const ColPlan &p, uint32_t *__restrict__ dst,
                                           uint32_t *__restrict__ dst2) {
-    for (int base = row0; base < W; base += ROWS_IN_FLIGHT * stride) {
+    const int nk = ceil_div_pos(W - row0, stride);               // rows owned by this lane
+    const int k_lo = min(ceil_div_pos(-i0 - row0, stride), nk);  // first k with i0 + row >= 0
+    const int k_hi = min(ceil_div_pos(G - i0 - row0, stride), nk);   // first k with i0 + row >= G
+    const int dstep = stride * wpr;
+    int d = row0 * wpr + wl;
+    for (int k = 0; k < k_lo; ++k, d += dstep) {
+        __stcs(dst + d, 0xFFFFFFFFu);
+        if (TWO) __stcs(dst2 + d, 0xFFFFFFFFu);
+    }
+    const uint32_t *img32 = reinterpret_cast<const uint32_t *>(img);
+    const int sstep = (stride * G) >> 2;
+    int s_lo = ((i0 + row0 + k_lo * stride) * G + p.off_lo) >> 2;
+    int s_hi = ((i0 + row0 + k_lo * stride) * G + p.off_hi) >> 2;
+    int k = k_lo;
+    for (; k + ROWS_IN_FLIGHT <= k_hi; k += ROWS_IN_FLIGHT) {
         uint32_t lo[ROWS_IN_FLIGHT], hi[ROWS_IN_FLIGHT];
 #pragma unroll
-        for (int k = 0; k < ROWS_IN_FLIGHT; ++k) {
-            const int row = base + k * stride, i = i0 + row;
-            lo[k] = 0xFFFFFFFFu; hi[k] = 0xFFFFFFFFu;
-            if (row < W && static_cast<unsigned>(i) < static_cast<unsigned>(G)) {
-                const uint8_t *src = img + static_cast<size_t>(i) * G;
-                lo[k] = __ldg(reinterpret_cast<const uint32_t *>(src + p.off_lo));
-                hi[k] = __ldg(reinterpret_cast<const uint32_t *>(src + p.off_hi));
-            }
+        for (int u = 0; u < ROWS_IN_FLIGHT; ++u) {
+            lo[u] = __ldg(img32 + s_lo + u * sstep);
+            hi[u] = __ldg(img32 + s_hi + u * sstep);
         }
 #pragma unroll
-        for (int k = 0; k < ROWS_IN_FLIGHT; ++k) {
-            const int row = base + k * stride;
-            if (row < W) {
-                const uint32_t v = __funnelshift_r(lo[k], hi[k], p.shift) | p.ormask;
-                __stcs(dst + row * wpr + wl, v);                 // streaming store: frames are write-once
-                if (dst2) __stcs(dst2 + row * wpr + wl, v);
-            }
+        for (int u = 0; u < ROWS_IN_FLIGHT; ++u) {
+            const uint32_t v = __funnelshift_r(lo[u], hi[u], p.shift) | p.ormask;
+            __stcs(dst + d + u * dstep, v);
+            if (TWO) __stcs(dst2 + d + u * dstep, v);
         }
+        s_lo += ROWS_IN_FLIGHT * sstep; s_hi += ROWS_IN_FLIGHT * sstep; d += ROWS_IN_FLIGHT * dstep;
+    }
+    {   // tail: fewer than ROWS_IN_FLIGHT in-grid rows left, still issued as one batch of loads
+        uint32_t lo[ROWS_IN_FLIGHT], hi[ROWS_IN_FLIGHT];
+        const int rem = k_hi - k;
+#pragma unroll
+        for (int u = 0; u < ROWS_IN_FLIGHT - 1; ++u)
+            if (u < rem) {
+                lo[u] = __ldg(img32 + s_lo + u * sstep);
+                hi[u] = __ldg(img32 + s_hi + u * sstep);
+            }
+#pragma unroll
+        for (int u = 0; u < ROWS_IN_FLIGHT - 1; ++u)
+            if (u < rem) {
+                const uint32_t v = __funnelshift_r(lo[u], hi[u], p.shift) | p.ormask;
+                __stcs(dst + d + u * dstep, v);
+                if (TWO) __stcs(dst2 + d + u * dstep, v);
+            }
+        d += rem * dstep;
+    }
+    for (k = k_hi; k < nk; ++k, d += dstep) {
+        __stcs(dst + d, 0xFFFFFFFFu);
+        if (TWO) __stcs(dst2 + d, 0xFFFFFFFFu);
     }
 }
 
@@ -221,18 +252,22 @@ __global__ void __launch_bounds__(128) observe_kernel(StepArgs a) {
         const int sub = lane / wpr, wl = lane - sub * wpr;
         if (sub >= rpi) return;
         const ColPlan pn = make_plan(G, j0 + 4 * wl);
-        crop_rows(img, G, W, wpr, i0, warp * rpi + sub, 4 * rpi, wl, pn, f_new, (two && same) ? f_old : nullptr);
-        if (two && !same) {
-            const ColPlan po = make_plan(G, q0 + 4 * wl);
-            crop_rows(img, G, W, wpr, p0, warp * rpi + sub, 4 * rpi, wl, po, f_old, nullptr);
+        if (two && same) {
+            crop_rows<true>(img, G, W, wpr, i0, warp * rpi + sub, 4 * rpi, wl, pn, f_new, f_old);
+        } else {
+            crop_rows<false>(img, G, W, wpr, i0, warp * rpi + sub, 4 * rpi, wl, pn, f_new, nullptr);
+            if (two) {
+                const ColPlan po = make_plan(G, q0 + 4 * wl);
+                crop_rows<false>(img, G, W, wpr, p0, warp * rpi + sub, 4 * rpi, wl, po, f_old, nullptr);
+            }
         }
     } else {
         for (int wl = lane; wl < wpr; wl += 32) {
             const ColPlan pn = make_plan(G, j0 + 4 * wl);
-            crop_rows(img, G, W, wpr, i0, warp, 4, wl, pn, f_new, (two && same) ? f_old : nullptr);
-            if (two && !same) {
+            crop_rows<false>(img, G, W, wpr, i0, warp, 4, wl, pn, f_new, nullptr);
+            if (two) {
                 const ColPlan po = make_plan(G, q0 + 4 * wl);
-                crop_rows(img, G, W, wpr, p0, warp, 4, wl, po, f_old, nullptr);
+                crop_rows<false>(img, G, W, wpr, p0, warp, 4, wl, po, f_old, nullptr);
             }
         }
     }
