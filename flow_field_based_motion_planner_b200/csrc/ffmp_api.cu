@@ -115,6 +115,8 @@ struct ffmp_handle {
     int p = 1;  // newest ring slot
     int ff_grid = 0, sc_grid = 0;   // full-batch grids (reset)
     int rg_grid = 0;                // background regeneration grid (few items per tick)
+    CUtensorMap tmap;               // flow planes as a 3-D u8 tensor for the TMA observe kernel
+    bool use_tma = false;
 
     uint32_t *error_word() const { return reinterpret_cast<uint32_t *>(static_cast<char *>(b.workspace) + ws.error_word); }
     char *list_base(int l) const { return static_cast<char *>(b.workspace) + ws.lists + ws.list_stride * l; }
@@ -180,7 +182,7 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
         a.slot_new = h->p; a.write_older = 0;
     }
     a.regen_env = h->list_env(l); a.regen_episode = h->list_episode(l); a.regen_count = h->list_count(l);
-    CK(ffmp::launch_step(a, st));
+    CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st));
     CK(cudaEventRecord(h->ev_step[l], st));
     CK(cudaStreamWaitEvent(h->side[l], h->ev_step[l], 0));
     ffmp::ScenarioArgs sa = scenario_args(h);
@@ -268,6 +270,31 @@ int ffmp_bind(ffmp_handle *h, const ffmp_buffers *bufs) {
     h->b = *bufs;
     h->bound = true;
     h->ready = false;
+    h->use_tma = false;
+    const ffmp_cfg &c = h->cfg;
+    if (c.grid % 16 == 0 && ((c.window + 30) & ~15) <= 256) {
+        // 3-D tensor map over the flow planes: dims (cols, rows, planes), box = ceil16(W+15) x W x 1, zero fill
+        typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        DeviceGuard guard(c.device);
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+            qres == cudaDriverEntryPointSuccess) {
+            const cuuint64_t G = static_cast<cuuint64_t>(c.grid);
+            const cuuint64_t dims[3] = {G, G, static_cast<cuuint64_t>(c.slots) * static_cast<cuuint64_t>(c.num_envs)};
+            const cuuint64_t strides[2] = {G, G * G};
+            const cuuint32_t box[3] = {static_cast<cuuint32_t>((c.window + 30) & ~15), static_cast<cuuint32_t>(c.window), 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = reinterpret_cast<EncodeFn>(fn)(&h->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, bufs->flow, dims, strides, box,
+                                                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            h->use_tma = r == CUDA_SUCCESS;
+        } else {
+            cudaGetLastError();
+        }
+    }
     return FFMP_OK;
 }
 
@@ -314,7 +341,7 @@ int ffmp_reset(ffmp_handle *h, const uint8_t *mask_dev, void *stream) {
     ffmp::StepArgs a = step_args(h);
     a.mode = 2; a.slot_new = 1; a.write_older = 1;
     a.regen_env = h->list_env(0); a.regen_episode = h->list_episode(0); a.regen_count = h->list_count(0);
-    CK(ffmp::launch_step(a, st));
+    CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st));
     h->ready = true;
     return FFMP_OK;
 }

@@ -273,6 +273,121 @@ __global__ void __launch_bounds__(128) observe_kernel(StepArgs a) {
     }
 }
 
+// ---- TMA variant of observe_kernel (G % 16 == 0) -------------------------------------------------------
+// One `cp.async.bulk.tensor.3d` per frame pulls the W-row window of the flow image into shared memory: the
+// TMA engine does the address generation and keeps ~13 KB per CTA in flight without a single register.  TMA
+// needs a 16-byte aligned inner coordinate, so the box starts at floor16(j0) and is ceil16(W+15) bytes wide;
+// the remaining 0..15 byte misalignment is removed while draining the tile (two LDS + funnel shift).
+// Out-of-grid bytes arrive as zeros and are turned into 255 with a per-lane column mask and a per-row mask.
+// The CTA streams the dense W x W frame to the ring with coalesced 32-bit stores.
+__device__ __forceinline__ void tma_window(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
+template <bool TWO>
+__device__ __forceinline__ void drain_tile(const uint32_t *__restrict__ tile32, int tile_wpr, int G, int W, int wpr,
+                                           int i0, int mis, int row0, int stride, int wl, uint32_t ormask,
+                                           uint32_t *__restrict__ dst, uint32_t *__restrict__ dst2) {
+    int s = row0 * tile_wpr + (mis >> 2) + wl, d = row0 * wpr + wl;
+    const int sstep = stride * tile_wpr, dstep = stride * wpr;
+    const int shift = 8 * (mis & 3);
+#pragma unroll 5
+    for (int row = row0; row < W; row += stride, s += sstep, d += dstep) {
+        const uint32_t rowmask = static_cast<unsigned>(i0 + row) >= static_cast<unsigned>(G) ? 0xFFFFFFFFu : 0u;
+        const uint32_t v = __funnelshift_r(tile32[s], tile32[s + 1], shift) | ormask | rowmask;
+        __stcs(dst + d, v);
+        if (TWO) __stcs(dst2 + d, v);
+    }
+}
+
+__global__ void __launch_bounds__(128) observe_tma_kernel(const __grid_constant__ CUtensorMap tmap, StepArgs a) {
+    extern __shared__ __align__(128) uint8_t tile[];
+    __shared__ __align__(8) uint64_t mbar;
+    const int e = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int G = a.G, W = a.W;
+    const int wpr = W >> 2;
+    const int tile_w = (W + 15 + 15) & ~15;                   // TMA box inner extent: W + worst misalignment, multiple of 16
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&mbar));
+    const uint32_t tile_s = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const uint32_t *ob = a.obs_order + static_cast<size_t>(e) * OB_WORDS;
+    const uint4 o0 = *reinterpret_cast<const uint4 *>(ob);
+    const uint2 o1 = *reinterpret_cast<const uint2 *>(ob + 4);
+    if (!(o1.y & 1u)) return;
+    const bool two = (o1.y & 2u) != 0;
+    const int ci = static_cast<int>(o0.x), cj = static_cast<int>(o0.y), pi = static_cast<int>(o0.z), pj = static_cast<int>(o0.w);
+    const bool same = pi == ci && pj == cj;
+    const int i0 = ci - (W >> 1), j0 = cj - (W >> 1);
+    const uint32_t bytes = static_cast<uint32_t>(tile_w * W);
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        tma_window(tile_s, &tmap, j0 & ~15, i0, static_cast<int>(o1.x), bar);
+    }
+    uint32_t *f_new = reinterpret_cast<uint32_t *>(a.frames + (static_cast<size_t>(e) * a.K + a.slot_new) * W * W);
+    uint32_t *f_old = f_new - (W * W >> 2);
+    // lane -> (row slot, word) mapping and the column mask (out-of-grid columns -> 255)
+    int rpi = 1, sub = 0, wl = lane;
+    if (wpr <= 32) { rpi = 32 / wpr; sub = lane / wpr; wl = lane - sub * wpr; }
+    auto colmask = [&](int jbase, int w) {
+        uint32_t om = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (static_cast<unsigned>(jbase + 4 * w + c) >= static_cast<unsigned>(G)) om |= 0xFFu << (8 * c);
+        return om;
+    };
+    const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
+    const int tile_wpr = tile_w >> 2;
+    // wait for the window (phase 0)
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+    }
+    if (wpr <= 32) {
+        if (sub < rpi) {
+            const uint32_t om = colmask(j0, wl);
+            if (two && same) drain_tile<true>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, warp * rpi + sub, 4 * rpi, wl, om, f_new, f_old);
+            else drain_tile<false>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, warp * rpi + sub, 4 * rpi, wl, om, f_new, nullptr);
+        }
+    } else {
+        for (int w2 = lane; w2 < wpr; w2 += 32)
+            drain_tile<false>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, warp, 4, w2, colmask(j0, w2), f_new, nullptr);
+        if (two && same)
+            for (int w2 = lane; w2 < wpr; w2 += 32)
+                drain_tile<false>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, warp, 4, w2, colmask(j0, w2), f_old, nullptr);
+    }
+    if (two && !same) {
+        // older frame of a non-reset env on a ring wrap: the window at the previous pose
+        const int p0 = pi - (W >> 1), q0 = pj - (W >> 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of `tile` before the async overwrite
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            tma_window(tile_s, &tmap, q0 & ~15, p0, static_cast<int>(o1.x), bar);
+        }
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(1u) : "memory");
+        if (wpr <= 32) {
+            if (sub < rpi)
+                drain_tile<false>(tile32, tile_wpr, G, W, wpr, p0, q0 & 15, warp * rpi + sub, 4 * rpi, wl, colmask(q0, wl), f_old, nullptr);
+        } else {
+            for (int w2 = lane; w2 < wpr; w2 += 32)
+                drain_tile<false>(tile32, tile_wpr, G, W, wpr, p0, q0 & 15, warp, 4, w2, colmask(q0, w2), f_old, nullptr);
+        }
+    }
+}
+
 // Batched FFMP.rewarder / rewarder2 / reward_calculator (ffmp.py:130-188): one warp per item.
 __global__ void __launch_bounds__(128) rewarder_kernel(RewarderArgs a) {
     const int item = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -307,22 +422,33 @@ __global__ void __launch_bounds__(128) rewarder_kernel(RewarderArgs a) {
 
 }  // namespace
 
-cudaError_t launch_step(const StepArgs &a, cudaStream_t st) {
+cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t st) {
     if (a.N <= 0) return cudaSuccess;
     dynamics_kernel<<<(a.N + 127) / 128, 128, 0, st>>>(a);
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return ce;
-    // programmatic dependent launch: observe_kernel's CTAs become resident while dynamics_kernel drains
+    // programmatic dependent launch: the observe CTAs become resident while dynamics_kernel drains
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(a.N));
     cfg.blockDim = dim3(128);
-    cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (tmap) {
+        const size_t smem = static_cast<size_t>((a.W + 30) & ~15) * a.W + 16;   // +16: the drain reads one word past a row
+        static size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            ce = cudaFuncSetAttribute(observe_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (ce != cudaSuccess) return ce;
+            configured = smem;
+        }
+        cfg.dynamicSmemBytes = smem;
+        return cudaLaunchKernelEx(&cfg, observe_tma_kernel, *tmap, a);
+    }
+    cfg.dynamicSmemBytes = 0;
     return cudaLaunchKernelEx(&cfg, observe_kernel, a);
 }
 
