@@ -113,7 +113,7 @@ struct ffmp_handle {
     bool regen_pending[MAX_LISTS];
     uint64_t step_index = 0;
     int p = 1;  // newest ring slot
-    int ff_grid = 0, sc_grid = 0;   // full-batch grids (reset)
+    int ff_grid = 0;                // full-batch grid (reset)
     int rg_grid = 0;                // background regeneration grid (few items per tick)
     CUtensorMap tmap;               // flow planes as a 3-D u8 tensor for the TMA observe kernel
     bool use_tma = false;
@@ -131,20 +131,14 @@ struct ffmp_handle {
 
 namespace {
 
-ffmp::ScenarioArgs scenario_args(const ffmp_handle *h) {
-    ffmp::ScenarioArgs a{};
-    const ffmp_cfg &c = h->cfg;
-    a.G = c.grid; a.goal_mode = c.goal_mode; a.block_shift = c.block_shift; a.slot_mode = 1; a.S = c.slots; a.N = c.num_envs;
-    a.p_thresh = c.p_thresh; a.env_id_base = c.env_id_base; a.seed = c.seed;
-    a.occ = h->b.occ; a.scen = h->b.scen;
-    return a;
-}
-
 ffmp::FlowArgs flow_args(const ffmp_handle *h) {
     ffmp::FlowArgs a{};
     const ffmp_cfg &c = h->cfg;
     a.G = c.grid; a.slot_mode = 1; a.S = c.slots; a.N = c.num_envs;
-    a.occ = h->b.occ; a.scen = h->b.scen; a.cost = h->b.cost; a.flow = h->b.flow;
+    a.scen = h->b.scen; a.cost = h->b.cost; a.flow = h->b.flow;
+    // scenario generation is fused into the flow-field kernel (no occupancy plane round trip)
+    a.generate = 1; a.goal_mode = c.goal_mode; a.block_shift = c.block_shift; a.p_thresh = c.p_thresh;
+    a.env_id_base = c.env_id_base; a.seed = c.seed; a.scen_out = h->b.scen;
     a.hi_scratch = h->hi_scratch();
     return a;
 }
@@ -185,9 +179,6 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
     CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st));
     CK(cudaEventRecord(h->ev_step[l], st));
     CK(cudaStreamWaitEvent(h->side[l], h->ev_step[l], 0));
-    ffmp::ScenarioArgs sa = scenario_args(h);
-    sa.env_idx = h->list_env(l); sa.episode = h->list_episode(l); sa.count_ptr = h->list_count(l);
-    CK(ffmp::launch_scenarios(sa, h->rg_grid, h->side[l]));
     ffmp::FlowArgs fa = flow_args(h);
     fa.env_idx = h->list_env(l); fa.episode = h->list_episode(l); fa.count_ptr = h->list_count(l);
     fa.ticket = h->list_ticket(l); fa.count_reset = h->list_count(l);
@@ -210,7 +201,6 @@ int ffmp_query_sizes(const ffmp_cfg *cfg, ffmp_sizes *out) {
     if (int rc = check_cfg(cfg)) return rc;
     if (!out) return fail(FFMP_ERR_ARG, "out is null");
     const size_t N = cfg->num_envs, G = cfg->grid, W = cfg->window, K = cfg->ring, S = cfg->slots;
-    out->occ = S * N * G * G;
     out->cost = S * N * G * G * sizeof(int32_t);
     out->flow = S * N * G * G;
     out->scen = S * N * ffmp::SC_WORDS * sizeof(uint32_t);
@@ -248,7 +238,6 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
     }
     const int maxg = ffmp::flow_field_max_grid(cfg->grid);
     h->ff_grid = cfg->num_envs < maxg ? cfg->num_envs : maxg;
-    h->sc_grid = cfg->num_envs < 148 * 8 ? cfg->num_envs : 148 * 8;
     h->rg_grid = cfg->num_envs < REGEN_GRID ? cfg->num_envs : REGEN_GRID;
     *out = h;
     return FFMP_OK;
@@ -256,12 +245,12 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
 
 int ffmp_bind(ffmp_handle *h, const ffmp_buffers *bufs) {
     if (!h || !bufs) return fail(FFMP_ERR_ARG, "null argument");
-    const void *ptrs[] = {bufs->occ, bufs->cost, bufs->flow, bufs->scen, bufs->state, bufs->frames, bufs->rel_goal,
+    const void *ptrs[] = {bufs->cost, bufs->flow, bufs->scen, bufs->state, bufs->frames, bufs->rel_goal,
                           bufs->velocity, bufs->reward, bufs->done, bufs->flags, bufs->term_rel_goal, bufs->term_velocity,
                           bufs->fin_return, bufs->fin_length, bufs->workspace};
     for (const void *p : ptrs)
         if (!p) return fail(FFMP_ERR_ARG, "every ffmp_buffers pointer must be set");
-    const uintptr_t aligned[] = {reinterpret_cast<uintptr_t>(bufs->occ), reinterpret_cast<uintptr_t>(bufs->cost),
+    const uintptr_t aligned[] = {reinterpret_cast<uintptr_t>(bufs->cost),
                                  reinterpret_cast<uintptr_t>(bufs->flow), reinterpret_cast<uintptr_t>(bufs->frames),
                                  reinterpret_cast<uintptr_t>(bufs->state), reinterpret_cast<uintptr_t>(bufs->scen),
                                  reinterpret_cast<uintptr_t>(bufs->workspace)};
@@ -329,9 +318,6 @@ int ffmp_reset(ffmp_handle *h, const uint8_t *mask_dev, void *stream) {
     CK(cudaMemsetAsync(h->b.state, 0, static_cast<size_t>(c.num_envs) * ffmp::ST_WORDS * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(h->b.workspace, 0, h->ws.actions, st));  // error word + regen lists
     for (int s = 0; s < c.slots; ++s) {
-        ffmp::ScenarioArgs sa = scenario_args(h);
-        sa.count = c.num_envs; sa.episode_const = static_cast<uint32_t>(s);
-        CK(ffmp::launch_scenarios(sa, h->sc_grid, st));
         ffmp::FlowArgs fa = flow_args(h);
         fa.count = c.num_envs; fa.episode_const = static_cast<uint32_t>(s);
         CK(ffmp::launch_flow_field(fa, h->ff_grid, st));

@@ -37,6 +37,11 @@ struct FlowArgs {
     uint32_t *hi_scratch;       // per-CTA spill area for cost bit-planes >= 8
     uint32_t *ticket;           // dev u32: CTA completion ticket (slot_mode) or null
     uint32_t *count_reset;      // dev u32 reset to 0 by the last CTA (the regen list counter) or null
+    // in-kernel scenario generation (generate = 1, slot_mode only): SPEC.md §3 parameters and the record output
+    int generate, goal_mode, block_shift;
+    uint32_t p_thresh, env_id_base;
+    uint64_t seed;
+    uint32_t *scen_out;
 };
 
 struct StepArgs {

@@ -87,7 +87,42 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int WPR>
+// 8x8 bit-matrix transpose of the 64-bit value hi:lo (Hacker's Delight 7-3), on 32-bit halves
+__device__ __forceinline__ void transpose8(uint32_t &lo, uint32_t &hi) {
+    uint32_t t;
+    t = (lo ^ (lo >> 7)) & 0x00AA00AAu; lo ^= t ^ (t << 7);
+    t = (hi ^ (hi >> 7)) & 0x00AA00AAu; hi ^= t ^ (t << 7);
+    t = (lo ^ (lo >> 14)) & 0x0000CCCCu; lo ^= t ^ (t << 14);
+    t = (hi ^ (hi >> 14)) & 0x0000CCCCu; hi ^= t ^ (t << 14);
+    t = (lo ^ __funnelshift_r(lo, hi, 28)) & 0xF0F0F0F0u;
+    lo ^= t; hi ^= t >> 4;
+}
+
+// 4x4 byte transpose: out[b] = (p0.b, p1.b, p2.b, p3.b)
+__device__ __forceinline__ void bytes4x4(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t (&out)[4]) {
+    const uint32_t a = __byte_perm(p0, p1, 0x5140), b = __byte_perm(p0, p1, 0x7362);
+    const uint32_t c = __byte_perm(p2, p3, 0x5140), d = __byte_perm(p2, p3, 0x7362);
+    out[0] = __byte_perm(a, c, 0x5410); out[1] = __byte_perm(a, c, 0x7632);
+    out[2] = __byte_perm(b, d, 0x5410); out[3] = __byte_perm(b, d, 0x7632);
+}
+
+__device__ __forceinline__ void cell_of(uint32_t u, int G, int &i, int &j) {
+    const uint32_t span = static_cast<uint32_t>(G - 6);
+    i = 3 + static_cast<int>((u & 0xFFFFu) % span);
+    j = 3 + static_cast<int>((u >> 16) % span);
+}
+
+// bits [lo, hi] (inclusive, clipped to this 32-column word starting at column c0) as a mask
+__device__ __forceinline__ uint32_t col_range_mask(int lo, int hi, int c0) {
+    lo = max(lo - c0, 0); hi = min(hi - c0, 31);
+    if (lo > hi) return 0u;
+    return (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
+}
+
+// GEN = true : the scenario (SPEC.md §3) is generated in-kernel from the hash RNG straight into the bit
+//              mask (no occupancy plane round trip); used by the batched env (reset and regeneration).
+// GEN = false: the occupancy plane is an input (stateless operator), staged with one TMA bulk copy.
+template <int WPR, bool GEN>
 __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
     constexpr int RPL = WPR;                    // rows per lane
     constexpr int PLANE_WORDS = 32 * RPL * WPR;  // one bit-plane of the padded (32*WPR)^2 grid
@@ -102,77 +137,165 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
     uint32_t *hi = a.hi_scratch + static_cast<size_t>(blockIdx.x) * (8 * PLANE_WORDS);
     uint32_t parity = 0;
 
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (!GEN) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
     }
-    __syncwarp();
 
     auto pidx = [&](int k, int r, int ln) { return ((k * RPL + r) * 32 + ln) * WPR; };
 
     for (int item = blockIdx.x; item < count; item += gridDim.x) {
         const uint32_t env = a.env_idx ? a.env_idx[item] : static_cast<uint32_t>(item);
+        const size_t cells = static_cast<size_t>(G) * G;
         size_t plane;
         int gi, gj;
-        if (a.slot_mode) {
-            plane = static_cast<size_t>((a.episode ? a.episode[item] : a.episode_const) % a.S) * a.N + env;
-            gi = static_cast<int>(a.scen[plane * SC_WORDS + SC_GI]);
-            gj = static_cast<int>(a.scen[plane * SC_WORDS + SC_GJ]);
-        } else {
-            plane = static_cast<size_t>(item);
-            gi = a.goal_cells[2 * item];
-            gj = a.goal_cells[2 * item + 1];
-        }
-        const size_t cells = static_cast<size_t>(G) * G;
-
-        // ---- 1. TMA bulk copy of the occupancy plane into shared memory --------------------------
-        fence_proxy_async();  // earlier generic-proxy accesses to `pl` are ordered before the async write
-        __syncwarp();
-        if (lane == 0) {
-            mbar_expect_tx(bar, static_cast<uint32_t>(cells));
-            tma_bulk_g2s(pl_s, a.occ + plane * cells, static_cast<uint32_t>(cells), bar);
-        }
-        mbar_wait(bar, parity);
-        parity ^= 1;
-
-        // ---- 2. bytes -> free-cell bit mask (registers) -----------------------------------------
         uint32_t FR[RPL][WPR];
-        {
-            const uint8_t *stage = reinterpret_cast<const uint8_t *>(pl);
+
+        if (GEN) {
+            // ---- 1g. scenario parameters (lane 0) and the free-cell mask straight from the hash ---
+            const uint32_t episode = a.episode ? a.episode[item] : a.episode_const;
+            plane = static_cast<size_t>(episode % a.S) * a.N + env;
+            const uint32_t key = scenario_key(a.seed, a.env_id_base + env, episode);
+            int si = 0, sj = 0;
+            gi = 0; gj = 0;
+            if (lane == 0) {
+                if (a.goal_mode == 0) {
+                    cell_of(draw(key, S_START, 0), G, si, sj);
+                    for (uint32_t t = 0; t < 64; ++t) {
+                        cell_of(draw(key, S_GOAL, t), G, gi, gj);
+                        if ((gi - si) * (gi - si) + (gj - sj) * (gj - sj) >= 400) break;
+                    }
+                } else {
+                    gi = G - 8; gj = G - 8;
+                    for (uint32_t t = 0; t < 64; ++t) {
+                        cell_of(draw(key, S_START, t), G, si, sj);
+                        if ((gi - si) * (gi - si) + (gj - sj) * (gj - sj) >= 400) break;
+                    }
+                }
+                float yaw = fsub(fmul(static_cast<float>(draw(key, S_YAW, 0) >> 8), TWO_PI_F * 5.9604644775390625e-08f), PI_F);
+                yaw = pi_to_pi(yaw);
+                uint32_t *rec = a.scen_out + plane * SC_WORDS;
+                *reinterpret_cast<uint4 *>(rec) = make_uint4(__float_as_uint(fmul(static_cast<float>(si), RES)),
+                                                            __float_as_uint(fmul(static_cast<float>(sj), RES)), __float_as_uint(yaw),
+                                                            __float_as_uint(fmul(static_cast<float>(gi), RES)));
+                *reinterpret_cast<uint4 *>(rec + 4) = make_uint4(__float_as_uint(fmul(static_cast<float>(gj), RES)),
+                                                                static_cast<uint32_t>(gi), static_cast<uint32_t>(gj), key);
+            }
+            si = __shfl_sync(FULL, si, 0); sj = __shfl_sync(FULL, sj, 0);
+            gi = __shfl_sync(FULL, gi, 0); gj = __shfl_sync(FULL, gj, 0);
+            const int bs = a.block_shift;
+            const int bw = 1 << bs;                          // obstacle block width in cells
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                const int R = lane * RPL + r;
+                const bool interior_row = R > 0 && R < G - 1;
+                const bool near_s = abs(R - si) <= 2, near_g = abs(R - gi) <= 2;
+#pragma unroll
+                for (int w = 0; w < WPR; ++w) {
+                    const int c0 = 32 * w;
+                    uint32_t occ = 0;
+                    if (bw >= 32) {
+                        const uint32_t blk = (static_cast<uint32_t>(R >> bs) << 16) | static_cast<uint32_t>(c0 >> bs);
+                        occ = mix32(key + blk * 0x9E3779B1u) < a.p_thresh ? 0xFFFFFFFFu : 0u;
+                    } else {
+                        const uint32_t bmask = bw >= 32 ? 0xFFFFFFFFu : ((1u << bw) - 1u);
+                        for (int c = 0; c < 32; c += bw) {
+                            const uint32_t blk = (static_cast<uint32_t>(R >> bs) << 16) | static_cast<uint32_t>((c0 + c) >> bs);
+                            if (mix32(key + blk * 0x9E3779B1u) < a.p_thresh) occ |= bmask << c;
+                        }
+                    }
+                    uint32_t fr = ~occ;
+                    if (near_s) fr |= col_range_mask(sj - 2, sj + 2, c0);          // cleared 5x5 around the start
+                    if (near_g) fr |= col_range_mask(gj - 2, gj + 2, c0);          // ... and around the goal
+                    fr &= col_range_mask(1, G - 2, c0);                             // border columns / padding
+                    FR[r][w] = interior_row ? fr : 0u;                              // border rows / padding rows
+                }
+            }
+        } else {
+            if (a.slot_mode) {
+                plane = static_cast<size_t>((a.episode ? a.episode[item] : a.episode_const) % a.S) * a.N + env;
+                gi = static_cast<int>(a.scen[plane * SC_WORDS + SC_GI]);
+                gj = static_cast<int>(a.scen[plane * SC_WORDS + SC_GJ]);
+            } else {
+                plane = static_cast<size_t>(item);
+                gi = a.goal_cells[2 * item];
+                gj = a.goal_cells[2 * item + 1];
+            }
+            // ---- 1. TMA bulk copy of the occupancy plane into shared memory ----------------------
+            fence_proxy_async();  // earlier generic-proxy accesses to `pl` are ordered before the async write
+            __syncwarp();
+            if (lane == 0) {
+                mbar_expect_tx(bar, static_cast<uint32_t>(cells));
+                tma_bulk_g2s(pl_s, a.occ + plane * cells, static_cast<uint32_t>(cells), bar);
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1;
+
+            // ---- 2. bytes -> free-cell bit mask (registers) --------------------------------------
+            if (G == 32 * WPR) {
+                // bit packing is linear in the flat cell index: every lane packs 16 consecutive bytes into
+                // 16 bits (conflict-free LDS.128), written in place at byte f/8; each lane then owns the
+                // WPR*WPR consecutive words of its rows
+                uint8_t *stage = reinterpret_cast<uint8_t *>(pl);
 #pragma unroll 1
-            for (int o = 0; o < 32; ++o) {
+                for (int it = 0; it < (32 * WPR * WPR) / 16; ++it) {
+                    const int f = 16 * (32 * it + lane);
+                    const uint4 q = *reinterpret_cast<const uint4 *>(stage + f);
+                    const uint32_t x4[4] = {q.x, q.y, q.z, q.w};
+                    uint32_t bits = 0;
 #pragma unroll
-                for (int r = 0; r < RPL; ++r) {
-                    const int R = o * RPL + r;
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t x = x4[u];
+                        const uint32_t nz = (x | ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu)) & 0x80808080u;   // 0x80 per non-zero byte
+                        const uint32_t fr = (~nz >> 7) & 0x01010101u;
+                        bits |= ((fr * 0x01020408u) >> 24 & 0xFu) << (4 * u);
+                    }
+                    __syncwarp();
+                    *reinterpret_cast<uint16_t *>(stage + (f >> 3)) = static_cast<uint16_t>(bits);
+                    __syncwarp();
+                }
 #pragma unroll
-                    for (int w = 0; w < WPR; ++w) {
-                        const int col = 32 * w + lane;
-                        const bool fr = (R < G && col < G) ? stage[R * G + col] == 0 : false;
-                        const uint32_t bits = __ballot_sync(FULL, fr);
-                        if (lane == o) FR[r][w] = bits;
+                for (int r = 0; r < RPL; ++r) Row<WPR>::ld(&pl[(lane * RPL + r) * WPR], FR[r]);
+            } else {
+                const uint8_t *stage = reinterpret_cast<const uint8_t *>(pl);
+#pragma unroll 1
+                for (int o = 0; o < 32; ++o) {
+#pragma unroll
+                    for (int r = 0; r < RPL; ++r) {
+                        const int R = o * RPL + r;
+#pragma unroll
+                        for (int w = 0; w < WPR; ++w) {
+                            const int col = 32 * w + lane;
+                            const bool fr = (R < G && col < G) ? stage[R * G + col] == 0 : false;
+                            const uint32_t bits = __ballot_sync(FULL, fr);
+                            if (lane == o) FR[r][w] = bits;
+                        }
                     }
                 }
             }
+            __syncwarp();
         }
-        __syncwarp();
 
-        // ---- 3. zero the resident bit-planes -----------------------------------------------------
+        // ---- 3. zero the resident bit-planes 2.. (planes 0 and 1 live in registers during the BFS) ----
         {
             uint32_t z[WPR];
 #pragma unroll
             for (int w = 0; w < WPR; ++w) z[w] = 0;
 #pragma unroll
-            for (int k = 0; k < NPL; ++k)
+            for (int k = 2; k < NPL; ++k)
 #pragma unroll
                 for (int r = 0; r < RPL; ++r) Row<WPR>::st(&pl[pidx(k, r, lane)], z);
         }
 
         // ---- 4. bit-parallel wavefront -----------------------------------------------------------
-        uint32_t A[RPL][WPR], F[RPL][WPR];
+        uint32_t A[RPL][WPR], F[RPL][WPR], G0[RPL][WPR], G1[RPL][WPR];
 #pragma unroll
         for (int r = 0; r < RPL; ++r)
 #pragma unroll
-            for (int w = 0; w < WPR; ++w) { A[r][w] = FR[r][w]; F[r][w] = 0; }
+            for (int w = 0; w < WPR; ++w) { A[r][w] = FR[r][w]; F[r][w] = 0; G0[r][w] = 0; G1[r][w] = 0; }
         if (gi >= 0 && gj >= 0 && gi < G && gj < G && lane == gi / RPL) {
 #pragma unroll
             for (int r = 0; r < RPL; ++r)
@@ -184,11 +307,22 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
                         A[r][w] &= ~m;
                     }
         }
+        const uint32_t upmask = lane == 0 ? 0u : 0xFFFFFFFFu, dnmask = lane == 31 ? 0u : 0xFFFFFFFFu;
         uint32_t L = 1;
         for (;; ++L) {
             // Gray bit-plane update: cells with cost >= L flip Gray bit ctz(L)
             const int k = __ffs(L) - 1;
-            if (k < NPL) {
+            if (k == 0) {
+#pragma unroll
+                for (int r = 0; r < RPL; ++r)
+#pragma unroll
+                    for (int w = 0; w < WPR; ++w) G0[r][w] ^= A[r][w];
+            } else if (k == 1) {
+#pragma unroll
+                for (int r = 0; r < RPL; ++r)
+#pragma unroll
+                    for (int w = 0; w < WPR; ++w) G1[r][w] ^= A[r][w];
+            } else if (k < NPL) {
 #pragma unroll
                 for (int r = 0; r < RPL; ++r) {
                     uint32_t v[WPR];
@@ -211,10 +345,8 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
             uint32_t upF[WPR], dnF[WPR];
 #pragma unroll
             for (int w = 0; w < WPR; ++w) {
-                upF[w] = __shfl_up_sync(FULL, F[RPL - 1][w], 1);
-                dnF[w] = __shfl_down_sync(FULL, F[0][w], 1);
-                if (lane == 0) upF[w] = 0;
-                if (lane == 31) dnF[w] = 0;
+                upF[w] = __shfl_up_sync(FULL, F[RPL - 1][w], 1) & upmask;
+                dnF[w] = __shfl_down_sync(FULL, F[0][w], 1) & dnmask;
             }
             uint32_t Nw[RPL][WPR];
             uint32_t any = 0;
@@ -233,6 +365,11 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
 #pragma unroll
                 for (int w = 0; w < WPR; ++w) { A[r][w] &= ~Nw[r][w]; F[r][w] = Nw[r][w]; }
             if (!__any_sync(FULL, any != 0)) break;
+        }
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            Row<WPR>::st(&pl[pidx(0, r, lane)], G0[r]);
+            Row<WPR>::st(&pl[pidx(1, r, lane)], G1[r]);
         }
         const uint32_t Lmax = L - 1;                       // deepest level that reached a cell
         const int kmax = 32 - __clz(Lmax);                  // number of significant cost bits
@@ -270,38 +407,73 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
         // ---- 6. expand the integration field to int32 and store ---------------------------------
         if (a.cost) {
             int32_t *cost = a.cost + plane * cells;
-            const int klo = kmax < NPL ? kmax : NPL;
+            if (kmax <= NPL) {
+                // fast path (depth < 256): 8 planes x 32 cells -> 32 bytes with 4x4 byte transposes (PRMT) and
+                // 8x8 bit-matrix transposes, then widened to int32 with INF for unreached cells
 #pragma unroll 1
-            for (int rw = 0; rw < RPL * WPR; ++rw) {
-                const int r = rw / WPR, w = rw - r * WPR;
-                const int R = lane * RPL + r;
-                if (R >= G || 32 * w >= G) continue;
-                uint32_t lo[8], hb[8];
+                for (int rw = 0; rw < RPL * WPR; ++rw) {
+                    const int r = rw / WPR, w = rw - r * WPR;
+                    const int R = lane * RPL + r;
+                    if (R >= G || 32 * w >= G) continue;
+                    uint32_t P[NPL];
 #pragma unroll
-                for (int n = 0; n < 8; ++n) { lo[n] = 0; hb[n] = 0; }
-#pragma unroll 1
-                for (int k = 0; k < klo; ++k) {
-                    const uint32_t word = pl[pidx(k, r, lane) + w];
+                    for (int k = 0; k < NPL; ++k) P[k] = k < kmax ? pl[pidx(k, r, lane) + w] : 0u;
+                    const uint32_t vis = hi[pidx(PVIS - NPL, r, lane) + w];
+                    uint32_t tl[4], th[4];
+                    bytes4x4(P[0], P[1], P[2], P[3], tl);
+                    bytes4x4(P[4], P[5], P[6], P[7], th);
+                    int32_t *dst = cost + static_cast<size_t>(R) * G + 32 * w;
 #pragma unroll
-                    for (int n = 0; n < 8; ++n) lo[n] += spread4(word, n) << k;
+                    for (int b = 0; b < 4; ++b) {
+                        if (32 * w + 8 * b >= G) continue;
+                        uint32_t lo = tl[b], hb = th[b];
+                        transpose8(lo, hb);          // byte j of hb:lo = cost of cell 8b+j
+                        int4 c0, c1;
+                        c0.x = (vis >> (8 * b + 0)) & 1 ? static_cast<int>(lo & 0xFF) : COST_INF;
+                        c0.y = (vis >> (8 * b + 1)) & 1 ? static_cast<int>((lo >> 8) & 0xFF) : COST_INF;
+                        c0.z = (vis >> (8 * b + 2)) & 1 ? static_cast<int>((lo >> 16) & 0xFF) : COST_INF;
+                        c0.w = (vis >> (8 * b + 3)) & 1 ? static_cast<int>(lo >> 24) : COST_INF;
+                        c1.x = (vis >> (8 * b + 4)) & 1 ? static_cast<int>(hb & 0xFF) : COST_INF;
+                        c1.y = (vis >> (8 * b + 5)) & 1 ? static_cast<int>((hb >> 8) & 0xFF) : COST_INF;
+                        c1.z = (vis >> (8 * b + 6)) & 1 ? static_cast<int>((hb >> 16) & 0xFF) : COST_INF;
+                        c1.w = (vis >> (8 * b + 7)) & 1 ? static_cast<int>(hb >> 24) : COST_INF;
+                        *reinterpret_cast<int4 *>(dst + 8 * b) = c0;
+                        if (32 * w + 8 * b + 4 < G) *reinterpret_cast<int4 *>(dst + 8 * b + 4) = c1;
+                    }
                 }
+            } else {
 #pragma unroll 1
-                for (int k = NPL; k < kmax; ++k) {
-                    const uint32_t word = hi[pidx(k - NPL, r, lane) + w];
+                for (int rw = 0; rw < RPL * WPR; ++rw) {
+                    const int r = rw / WPR, w = rw - r * WPR;
+                    const int R = lane * RPL + r;
+                    if (R >= G || 32 * w >= G) continue;
+                    uint32_t lo[8], hb[8];
 #pragma unroll
-                    for (int n = 0; n < 8; ++n) hb[n] += spread4(word, n) << (k - NPL);
-                }
-                const uint32_t vis = hi[pidx(PVIS - NPL, r, lane) + w];
-                int32_t *dst = cost + static_cast<size_t>(R) * G + 32 * w;
+                    for (int n = 0; n < 8; ++n) { lo[n] = 0; hb[n] = 0; }
+#pragma unroll 1
+                    for (int k = 0; k < NPL; ++k) {
+                        const uint32_t word = pl[pidx(k, r, lane) + w];
 #pragma unroll
-                for (int n = 0; n < 8; ++n) {
-                    if (32 * w + 4 * n >= G) continue;
-                    int4 c;
-                    c.x = (vis >> (4 * n + 0)) & 1 ? static_cast<int>((lo[n] & 0xFF) | ((hb[n] & 0xFF) << 8)) : COST_INF;
-                    c.y = (vis >> (4 * n + 1)) & 1 ? static_cast<int>(((lo[n] >> 8) & 0xFF) | (((hb[n] >> 8) & 0xFF) << 8)) : COST_INF;
-                    c.z = (vis >> (4 * n + 2)) & 1 ? static_cast<int>(((lo[n] >> 16) & 0xFF) | (((hb[n] >> 16) & 0xFF) << 8)) : COST_INF;
-                    c.w = (vis >> (4 * n + 3)) & 1 ? static_cast<int>((lo[n] >> 24) | ((hb[n] >> 24) << 8)) : COST_INF;
-                    *reinterpret_cast<int4 *>(dst + 4 * n) = c;
+                        for (int n = 0; n < 8; ++n) lo[n] += spread4(word, n) << k;
+                    }
+#pragma unroll 1
+                    for (int k = NPL; k < kmax; ++k) {
+                        const uint32_t word = hi[pidx(k - NPL, r, lane) + w];
+#pragma unroll
+                        for (int n = 0; n < 8; ++n) hb[n] += spread4(word, n) << (k - NPL);
+                    }
+                    const uint32_t vis = hi[pidx(PVIS - NPL, r, lane) + w];
+                    int32_t *dst = cost + static_cast<size_t>(R) * G + 32 * w;
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) {
+                        if (32 * w + 4 * n >= G) continue;
+                        int4 c;
+                        c.x = (vis >> (4 * n + 0)) & 1 ? static_cast<int>((lo[n] & 0xFF) | ((hb[n] & 0xFF) << 8)) : COST_INF;
+                        c.y = (vis >> (4 * n + 1)) & 1 ? static_cast<int>(((lo[n] >> 8) & 0xFF) | (((hb[n] >> 8) & 0xFF) << 8)) : COST_INF;
+                        c.z = (vis >> (4 * n + 2)) & 1 ? static_cast<int>(((lo[n] >> 16) & 0xFF) | (((hb[n] >> 16) & 0xFF) << 8)) : COST_INF;
+                        c.w = (vis >> (4 * n + 3)) & 1 ? static_cast<int>((lo[n] >> 24) | ((hb[n] >> 24) << 8)) : COST_INF;
+                        *reinterpret_cast<int4 *>(dst + 4 * n) = c;
+                    }
                 }
             }
         }
@@ -439,12 +611,22 @@ int flow_field_max_grid(int G) {
 cudaError_t launch_flow_field(const FlowArgs &a, int grid, cudaStream_t st) {
     if (grid <= 0) return cudaSuccess;
     const int wpr = (a.G + 31) / 32;
-    switch (wpr) {
-    case 1: flow_field_warp_kernel<1><<<grid, 32, 0, st>>>(a); break;
-    case 2: flow_field_warp_kernel<2><<<grid, 32, 0, st>>>(a); break;
-    case 3: flow_field_warp_kernel<3><<<grid, 32, 0, st>>>(a); break;
-    case 4: flow_field_warp_kernel<4><<<grid, 32, 0, st>>>(a); break;
-    default: return cudaErrorInvalidValue;
+    if (a.generate) {
+        switch (wpr) {
+        case 1: flow_field_warp_kernel<1, true><<<grid, 32, 0, st>>>(a); break;
+        case 2: flow_field_warp_kernel<2, true><<<grid, 32, 0, st>>>(a); break;
+        case 3: flow_field_warp_kernel<3, true><<<grid, 32, 0, st>>>(a); break;
+        case 4: flow_field_warp_kernel<4, true><<<grid, 32, 0, st>>>(a); break;
+        default: return cudaErrorInvalidValue;
+        }
+    } else {
+        switch (wpr) {
+        case 1: flow_field_warp_kernel<1, false><<<grid, 32, 0, st>>>(a); break;
+        case 2: flow_field_warp_kernel<2, false><<<grid, 32, 0, st>>>(a); break;
+        case 3: flow_field_warp_kernel<3, false><<<grid, 32, 0, st>>>(a); break;
+        case 4: flow_field_warp_kernel<4, false><<<grid, 32, 0, st>>>(a); break;
+        default: return cudaErrorInvalidValue;
+        }
     }
     return cudaGetLastError();
 }

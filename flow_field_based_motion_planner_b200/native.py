@@ -33,12 +33,12 @@ class Cfg(C.Structure):
 
 class Sizes(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in
-                ("occ", "cost", "flow", "scen", "state", "frames", "vec2", "vec1", "bytes1", "workspace")]
+                ("cost", "flow", "scen", "state", "frames", "vec2", "vec1", "bytes1", "workspace")]
 
 
 class Buffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("occ", "cost", "flow", "scen", "state", "frames", "rel_goal", "velocity", "reward", "done", "flags",
+                ("cost", "flow", "scen", "state", "frames", "rel_goal", "velocity", "reward", "done", "flags",
                  "term_rel_goal", "term_velocity", "fin_return", "fin_length", "workspace")]
 
 

@@ -101,7 +101,6 @@ class FFMPVectorEnv:
         N, G, W, K, S = cfg.num_envs, cfg.grid, cfg.window, cfg.ring, cfg.slots
         d = self.device
         with torch.cuda.device(d):
-            self.occ = torch.zeros((S, N, G, G), dtype=torch.uint8, device=d)
             self.cost = torch.zeros((S, N, G, G), dtype=torch.int32, device=d)
             self.flow = torch.zeros((S, N, G, G), dtype=torch.uint8, device=d)
             self.scen = torch.zeros((S, N, 8), dtype=torch.int32, device=d)
@@ -117,9 +116,9 @@ class FFMPVectorEnv:
             self.fin_return = torch.zeros((N,), dtype=torch.float32, device=d)
             self.fin_length = torch.zeros((N,), dtype=torch.int32, device=d)
             self._workspace = torch.zeros((sz.workspace,), dtype=torch.uint8, device=d)
-        assert self.occ.numel() == sz.occ and self.cost.numel() * 4 == sz.cost and self.frames.numel() == sz.frames
+        assert self.flow.numel() == sz.flow and self.cost.numel() * 4 == sz.cost and self.frames.numel() == sz.frames
         b = native.Buffers(**{name: getattr(self, name).data_ptr() for name in
-                              ("occ", "cost", "flow", "scen", "state", "frames", "rel_goal", "velocity", "reward",
+                              ("cost", "flow", "scen", "state", "frames", "rel_goal", "velocity", "reward",
                                "done", "flags", "term_rel_goal", "term_velocity", "fin_return", "fin_length")},
                            workspace=self._workspace.data_ptr())
         native.check(self._L.ffmp_bind(self._h, C.byref(b)), "ffmp_bind")
@@ -256,8 +255,8 @@ class FFMPVectorEnv:
         return self._current(self.flow)
 
     def occupancy(self):
-        self.join()
-        return self._current(self.occ)
+        """Occupancy of every env's current scenario (uint8 0/1), decoded from the flow image (255 = occupied)."""
+        return (self.flow_image() == 255).to(torch.uint8)
 
     def flow_dir(self):
         """Direction codes 0..7, 8 = none (SPEC.md §5 decoding of the flow image)."""

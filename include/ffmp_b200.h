@@ -64,7 +64,6 @@ typedef struct ffmp_cfg {
 
 /* Byte sizes of every caller-allocated buffer for a given cfg (ffmp_query_sizes). */
 typedef struct ffmp_sizes {
-    size_t occ;            /* u8  [S][N][G][G]  occupancy planes                  */
     size_t cost;           /* i32 [S][N][G][G]  integration field                 */
     size_t flow;           /* u8  [S][N][G][G]  flow image (255 occ, else dir*28) */
     size_t scen;           /* u32 [S][N][8]     scenario records                  */
@@ -80,7 +79,6 @@ typedef struct ffmp_sizes {
  * State record layout (u32 words): 0 x 1 y 2 yaw 3 gx 4 gy 5 d_first 6 ep_return (all f32)
  *                                  7 steps(i32) 8 episode(u32) 9..15 reserved. */
 typedef struct ffmp_buffers {
-    uint8_t *occ;              /* dev */
     int32_t *cost;             /* dev */
     uint8_t *flow;             /* dev */
     uint32_t *scen;            /* dev */
@@ -112,8 +110,8 @@ int ffmp_destroy(ffmp_handle *h);
 int ffmp_reset(ffmp_handle *h, const uint8_t *mask_dev, void *stream);
 
 /* step: actions_dev = i64[N] ids in [0,28) (SPEC.md §1).  Writes every output buffer, auto-resets
- * finished envs, and queues the regeneration of their consumed scenario slot on an internal
- * background stream.  Replaces the per-tick body of train.py:531-682.                             */
+ * finished envs, and queues the regeneration of their consumed scenario slot (scenario generation fused
+ * into the flow-field kernel) on internal background streams.  Replaces the per-tick body of train.py:531-682.                             */
 int ffmp_step(ffmp_handle *h, const int64_t *actions_dev, void *stream);
 
 /* T back-to-back steps with actions_dev = i64[T][N]; identical to T ffmp_step calls. */

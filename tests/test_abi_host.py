@@ -33,8 +33,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert C.sizeof(native.Cfg) == 64
     assert native.Cfg.seed.offset == 48 and native.Cfg.dt.offset == 56
-    assert C.sizeof(native.Sizes) == 10 * C.sizeof(C.c_size_t)
-    assert C.sizeof(native.Buffers) == 16 * C.sizeof(C.c_void_p)
+    assert C.sizeof(native.Sizes) == 9 * C.sizeof(C.c_size_t)
+    assert C.sizeof(native.Buffers) == 15 * C.sizeof(C.c_void_p)
 
 
 def test_cfg_validation_without_gpu():
@@ -43,7 +43,7 @@ def test_cfg_validation_without_gpu():
     good = dict(abi_version=1, device=0, num_envs=8, grid=128, window=100, ring=8, slots=3, max_steps=200,
                 goal_mode=0, block_shift=3, p_thresh=1, env_id_base=0, seed=0, dt=0.1, reserved=0)
     assert L.ffmp_query_sizes(C.byref(native.Cfg(**good)), C.byref(sz)) == 0
-    assert sz.occ == 3 * 8 * 128 * 128 and sz.cost == 4 * sz.occ and sz.frames == 8 * 8 * 100 * 100
+    assert sz.flow == 3 * 8 * 128 * 128 and sz.cost == 4 * sz.flow and sz.frames == 8 * 8 * 100 * 100
     assert sz.state == 8 * 64 and sz.scen == 3 * 8 * 32 and sz.workspace > 0
     for key, bad in [("abi_version", 2), ("num_envs", 0), ("grid", 130), ("grid", 8), ("window", 102), ("ring", 1),
                      ("slots", 1), ("max_steps", 0), ("goal_mode", 2), ("dt", 0.0), ("grid", 512)]:
