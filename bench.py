@@ -245,7 +245,8 @@ def run_ours(a):
                "note": "FFMPVectorEnv.step_host: pinned int64 actions H2D, reward/done/flags/relative_goal/velocity D2H "
                        "and a stream sync every step; local_map observations stay on the device for the learner"}
 
-        # ---- roofline of the dominant kernel (step_kernel), timed live with CUDA events on its stream ----
+        # ---- roofline of the dominant kernel (the observe kernel), timed live with CUDA events recorded by the
+        #      library on the launching stream around each launch (ffmp_timing) ----
         if rank == 0:
             peaks = {}
             try:
@@ -253,24 +254,31 @@ def run_ours(a):
             except (OSError, ValueError):
                 pass
             peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
-            reps = 200
-            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            traffic = None
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("observe_kernel_dram_bytes_per_launch")
+            except (OSError, ValueError):
+                pass
             env.join()
             torch.cuda.synchronize()
-            for i in range(reps):
-                evs[i][0].record()
+            env.kernel_timing(True)
+            for i in range(250):
                 env.step(actions[i % chunk])
-                evs[i][1].record()
+            kt = env.kernel_timing(False)
+            env.join()
             torch.cuda.synchronize()
-            times = sorted(x.elapsed_time(y) for x, y in evs)
-            avg_ms = sum(times) / len(times)
-            bytes_per_launch = N * (2 * a.window * a.window + 146)
-            achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
-            roofline = {"kernel": "step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": None,
+            # 2*W^2 + 146 B per env-step; the observe kernel moves the 2*W^2 part, dynamics the 146 B
+            obs_bytes = N * 2 * a.window * a.window
+            achieved = obs_bytes / (kt["observe_ms"] * 1e-3) / 1e9
+            tick_bytes = N * (2 * a.window * a.window + 146)
+            tick_ms = kt["observe_ms"] + kt["dynamics_ms"]
+            roofline = {"kernel": "observe_tma_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": traffic,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback",
-                        "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
-                        "median_launch_ms": times[len(times) // 2]}
+                        "algorithmic_bytes_per_launch": obs_bytes, "avg_launch_ms": kt["observe_ms"], "launches_timed": kt["ticks"],
+                        "dynamics_kernel_avg_ms": kt["dynamics_ms"],
+                        "tick": {"algorithmic_bytes": tick_bytes, "ms": tick_ms,
+                                 "achieved": tick_bytes / (tick_ms * 1e-3) / 1e9, "frac": tick_bytes / (tick_ms * 1e-3) / 1e9 / peak}}
 
             # ---- flow-field operator: grid cells/s and fraction of the 6 B/cell roofline ----
             gids = torch.arange(N, device=dev)

@@ -68,7 +68,7 @@ int check_cfg(const ffmp_cfg *c) {
     if (c->abi_version != FFMP_ABI_VERSION) return fail(FFMP_ERR_ABI, "cfg.abi_version != FFMP_ABI_VERSION");
     if (c->num_envs <= 0) return fail(FFMP_ERR_ARG, "num_envs must be > 0");
     if (c->grid < 16 || c->grid > 1024 || (c->grid % 4)) return fail(FFMP_ERR_ARG, "grid must be a multiple of 4 in [16,1024]");
-    if (!ffmp::flow_field_supported(c->grid)) return fail(FFMP_ERR_ARG, "grid > 128 is not supported by this build");
+    if (!ffmp::flow_field_supported(c->grid)) return fail(FFMP_ERR_ARG, "grid must be <= 128, or a multiple of 32 up to 512");
     if (c->window < 4 || c->window > 256 || (c->window % 4)) return fail(FFMP_ERR_ARG, "window must be a multiple of 4 in [4,256]");
     if (c->ring < 2 || c->ring > 1024) return fail(FFMP_ERR_ARG, "ring must be in [2,1024]");
     if (c->slots < 2 || c->slots > MAX_LISTS + 1) return fail(FFMP_ERR_ARG, "slots must be in [2,8]");
@@ -117,6 +117,11 @@ struct ffmp_handle {
     int rg_grid = 0;                // background regeneration grid (few items per tick)
     CUtensorMap tmap;               // flow planes as a 3-D u8 tensor for the TMA observe kernel
     bool use_tma = false;
+    // optional per-kernel timing (ffmp_timing): event triplets [before dynamics, between, after observe]
+    static constexpr int TIMING_RING = 256;
+    bool timing = false;
+    int timing_n = 0;
+    cudaEvent_t tev[TIMING_RING][3];
 
     uint32_t *error_word() const { return reinterpret_cast<uint32_t *>(static_cast<char *>(b.workspace) + ws.error_word); }
     char *list_base(int l) const { return static_cast<char *>(b.workspace) + ws.lists + ws.list_stride * l; }
@@ -176,7 +181,14 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
         a.slot_new = h->p; a.write_older = 0;
     }
     a.regen_env = h->list_env(l); a.regen_episode = h->list_episode(l); a.regen_count = h->list_count(l);
-    CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st));
+    if (h->timing && h->timing_n < ffmp_handle::TIMING_RING) {
+        cudaEvent_t *t = h->tev[h->timing_n++];
+        CK(cudaEventRecord(t[0], st));
+        CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st, t[1]));
+        CK(cudaEventRecord(t[2], st));
+    } else {
+        CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st));
+    }
     CK(cudaEventRecord(h->ev_step[l], st));
     CK(cudaStreamWaitEvent(h->side[l], h->ev_step[l], 0));
     ffmp::FlowArgs fa = flow_args(h);
@@ -226,6 +238,7 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
     h->nlist = cfg->slots - 1;
     std::memset(&h->b, 0, sizeof(h->b));
     for (int i = 0; i < MAX_LISTS; ++i) { h->side[i] = nullptr; h->ev_step[i] = nullptr; h->ev_regen[i] = nullptr; h->regen_pending[i] = false; }
+    std::memset(h->tev, 0, sizeof(h->tev));
     cudaError_t ce = cudaSuccess;
     for (int i = 0; i < h->nlist && ce == cudaSuccess; ++i) {
         ce = cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking);
@@ -298,6 +311,9 @@ int ffmp_destroy(ffmp_handle *h) {
         if (h->ev_step[i]) cudaEventDestroy(h->ev_step[i]);
         if (h->ev_regen[i]) cudaEventDestroy(h->ev_regen[i]);
     }
+    if (h->tev[0][0])
+        for (int i = 0; i < ffmp_handle::TIMING_RING; ++i)
+            for (int j = 0; j < 3; ++j) cudaEventDestroy(h->tev[i][j]);
     delete h;
     return FFMP_OK;
 }
@@ -368,6 +384,34 @@ int ffmp_step_host(ffmp_handle *h, const int64_t *actions_host, float *reward_ho
     return FFMP_OK;
 }
 
+int ffmp_timing(ffmp_handle *h, int32_t enable, float *dynamics_ms, float *observe_ms, int32_t *ticks) {
+    if (!h) return fail(FFMP_ERR_ARG, "handle is null");
+    DeviceGuard guard(h->cfg.device);
+    if (enable) {
+        if (!h->tev[0][0])
+            for (int i = 0; i < ffmp_handle::TIMING_RING; ++i)
+                for (int j = 0; j < 3; ++j) CK(cudaEventCreate(&h->tev[i][j]));
+        h->timing = true;
+        h->timing_n = 0;
+        return FFMP_OK;
+    }
+    h->timing = false;
+    double d = 0, o = 0;
+    for (int i = 0; i < h->timing_n; ++i) {
+        float a = 0, b = 0;
+        CK(cudaEventSynchronize(h->tev[i][2]));
+        CK(cudaEventElapsedTime(&a, h->tev[i][0], h->tev[i][1]));
+        CK(cudaEventElapsedTime(&b, h->tev[i][1], h->tev[i][2]));
+        d += a; o += b;
+    }
+    const int n = h->timing_n > 0 ? h->timing_n : 1;
+    if (dynamics_ms) *dynamics_ms = static_cast<float>(d / n);
+    if (observe_ms) *observe_ms = static_cast<float>(o / n);
+    if (ticks) *ticks = h->timing_n;
+    h->timing_n = 0;
+    return FFMP_OK;
+}
+
 int ffmp_obs_slot(const ffmp_handle *h, int32_t *newest_slot) {
     if (!h || !newest_slot) return fail(FFMP_ERR_ARG, "null argument");
     *newest_slot = h->p;
@@ -409,6 +453,7 @@ int ffmp_op_scenarios(int32_t device, int32_t n, int32_t G, uint32_t p_thresh, i
 
 size_t ffmp_op_flow_field_workspace(int32_t n, int32_t G) {
     if (n <= 0 || !ffmp::flow_field_supported(G)) return 0;
+    if (G > 128) return 16;
     const int maxg = ffmp::flow_field_max_grid(G);
     return static_cast<size_t>(n < maxg ? n : maxg) * ffmp::flow_field_scratch_words(G) * 4;
 }
@@ -416,7 +461,8 @@ size_t ffmp_op_flow_field_workspace(int32_t n, int32_t G) {
 int ffmp_op_flow_field(int32_t device, int32_t n, int32_t G, const uint8_t *occ_dev, const int32_t *goal_cells_dev,
                        int32_t *cost_dev, uint8_t *flow_dev, void *workspace_dev, void *stream) {
     if (n < 0 || !occ_dev || !goal_cells_dev || !flow_dev || !workspace_dev) return fail(FFMP_ERR_ARG, "bad argument");
-    if (!ffmp::flow_field_supported(G)) return fail(FFMP_ERR_ARG, "G must be a multiple of 4 in [16,128]");
+    if (!ffmp::flow_field_supported(G)) return fail(FFMP_ERR_ARG, "G must be a multiple of 4 in [16,128] or a multiple of 32 in (128,512]");
+    if (G > 128 && !cost_dev) return fail(FFMP_ERR_ARG, "the large-map kernel needs the cost plane (cost_dev != NULL)");
     if (reinterpret_cast<uintptr_t>(occ_dev) % 16 || reinterpret_cast<uintptr_t>(flow_dev) % 16 ||
         reinterpret_cast<uintptr_t>(cost_dev) % 16)
         return fail(FFMP_ERR_ARG, "occ / cost / flow must be 16-byte aligned");

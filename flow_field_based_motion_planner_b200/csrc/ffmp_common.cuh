@@ -112,6 +112,74 @@ __device__ __forceinline__ int robot_cell(float x) {
     return static_cast<int>(floorf(fadd(fmul(x, INV_RES), 0.5f)));
 }
 
+// ---- SPEC.md §3 scenario sampling (shared by scenario.cu and the flow-field kernels) -------------
+__device__ __forceinline__ void cell_of(uint32_t u, int G, int &i, int &j) {
+    const uint32_t span = static_cast<uint32_t>(G - 6);
+    i = 3 + static_cast<int>((u & 0xFFFFu) % span);
+    j = 3 + static_cast<int>((u >> 16) % span);
+}
+
+struct ScenarioParams {
+    int si, sj, gi, gj;
+    float yaw;
+};
+
+__device__ __forceinline__ ScenarioParams sample_scenario(uint32_t key, int G, int goal_mode) {
+    ScenarioParams p;
+    if (goal_mode == 0) {
+        cell_of(draw(key, S_START, 0), G, p.si, p.sj);
+        for (uint32_t t = 0; t < 64; ++t) {
+            cell_of(draw(key, S_GOAL, t), G, p.gi, p.gj);
+            if ((p.gi - p.si) * (p.gi - p.si) + (p.gj - p.sj) * (p.gj - p.sj) >= 400) break;
+        }
+    } else {
+        p.gi = G - 8; p.gj = G - 8;
+        for (uint32_t t = 0; t < 64; ++t) {
+            cell_of(draw(key, S_START, t), G, p.si, p.sj);
+            if ((p.gi - p.si) * (p.gi - p.si) + (p.gj - p.sj) * (p.gj - p.sj) >= 400) break;
+        }
+    }
+    p.yaw = pi_to_pi(fsub(fmul(static_cast<float>(draw(key, S_YAW, 0) >> 8), TWO_PI_F * 5.9604644775390625e-08f), PI_F));
+    return p;
+}
+
+__device__ __forceinline__ void store_scenario_record(uint32_t *rec, const ScenarioParams &p, uint32_t key) {
+    *reinterpret_cast<uint4 *>(rec) = make_uint4(__float_as_uint(fmul(static_cast<float>(p.si), RES)),
+                                                __float_as_uint(fmul(static_cast<float>(p.sj), RES)), __float_as_uint(p.yaw),
+                                                __float_as_uint(fmul(static_cast<float>(p.gi), RES)));
+    *reinterpret_cast<uint4 *>(rec + 4) = make_uint4(__float_as_uint(fmul(static_cast<float>(p.gj), RES)),
+                                                    static_cast<uint32_t>(p.gi), static_cast<uint32_t>(p.gj), key);
+}
+
+// bits [lo, hi] (inclusive, clipped to the 32-column word starting at column c0) as a mask
+__device__ __forceinline__ uint32_t col_range_mask(int lo, int hi, int c0) {
+    lo = max(lo - c0, 0); hi = min(hi - c0, 31);
+    if (lo > hi) return 0u;
+    return (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
+}
+
+// free-cell mask of the 32 cells (row R, columns c0..c0+31) of a generated scenario (bit = 1: free)
+__device__ __forceinline__ uint32_t scenario_free_word(uint32_t key, int R, int c0, int G, int bs, uint32_t p_thresh,
+                                                       const ScenarioParams &p) {
+    if (R <= 0 || R >= G - 1) return 0u;                                    // border rows / padding rows
+    const int bw = 1 << bs;
+    uint32_t occ = 0;
+    if (bw >= 32) {
+        const uint32_t blk = (static_cast<uint32_t>(R >> bs) << 16) | static_cast<uint32_t>(c0 >> bs);
+        occ = mix32(key + blk * 0x9E3779B1u) < p_thresh ? 0xFFFFFFFFu : 0u;
+    } else {
+        const uint32_t bmask = (1u << bw) - 1u;
+        for (int c = 0; c < 32; c += bw) {
+            const uint32_t blk = (static_cast<uint32_t>(R >> bs) << 16) | static_cast<uint32_t>((c0 + c) >> bs);
+            if (mix32(key + blk * 0x9E3779B1u) < p_thresh) occ |= bmask << c;
+        }
+    }
+    uint32_t fr = ~occ;
+    if (abs(R - p.si) <= 2) fr |= col_range_mask(p.sj - 2, p.sj + 2, c0);   // cleared 5x5 around the start
+    if (abs(R - p.gi) <= 2) fr |= col_range_mask(p.gj - 2, p.gj + 2, c0);   // ... and around the goal
+    return fr & col_range_mask(1, G - 2, c0);                               // border columns / padding
+}
+
 // SPEC.md §1 action table (robot/config.py:25-58)
 __device__ __forceinline__ void action_lookup(int a, float &v, float &w) {
     const int iv = a / 7, iw = a - 7 * iv;

@@ -106,19 +106,6 @@ __device__ __forceinline__ void bytes4x4(uint32_t p0, uint32_t p1, uint32_t p2, 
     out[2] = __byte_perm(b, d, 0x5410); out[3] = __byte_perm(b, d, 0x7632);
 }
 
-__device__ __forceinline__ void cell_of(uint32_t u, int G, int &i, int &j) {
-    const uint32_t span = static_cast<uint32_t>(G - 6);
-    i = 3 + static_cast<int>((u & 0xFFFFu) % span);
-    j = 3 + static_cast<int>((u >> 16) % span);
-}
-
-// bits [lo, hi] (inclusive, clipped to this 32-column word starting at column c0) as a mask
-__device__ __forceinline__ uint32_t col_range_mask(int lo, int hi, int c0) {
-    lo = max(lo - c0, 0); hi = min(hi - c0, 31);
-    if (lo > hi) return 0u;
-    return (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
-}
-
 // GEN = true : the scenario (SPEC.md §3) is generated in-kernel from the hash RNG straight into the bit
 //              mask (no occupancy plane round trip); used by the batched env (reset and regeneration).
 // GEN = false: the occupancy plane is an input (stateless operator), staged with one TMA bulk copy.
@@ -159,61 +146,20 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
             const uint32_t episode = a.episode ? a.episode[item] : a.episode_const;
             plane = static_cast<size_t>(episode % a.S) * a.N + env;
             const uint32_t key = scenario_key(a.seed, a.env_id_base + env, episode);
-            int si = 0, sj = 0;
-            gi = 0; gj = 0;
+            ScenarioParams sp;
+            sp.si = sp.sj = sp.gi = sp.gj = 0; sp.yaw = 0.0f;
             if (lane == 0) {
-                if (a.goal_mode == 0) {
-                    cell_of(draw(key, S_START, 0), G, si, sj);
-                    for (uint32_t t = 0; t < 64; ++t) {
-                        cell_of(draw(key, S_GOAL, t), G, gi, gj);
-                        if ((gi - si) * (gi - si) + (gj - sj) * (gj - sj) >= 400) break;
-                    }
-                } else {
-                    gi = G - 8; gj = G - 8;
-                    for (uint32_t t = 0; t < 64; ++t) {
-                        cell_of(draw(key, S_START, t), G, si, sj);
-                        if ((gi - si) * (gi - si) + (gj - sj) * (gj - sj) >= 400) break;
-                    }
-                }
-                float yaw = fsub(fmul(static_cast<float>(draw(key, S_YAW, 0) >> 8), TWO_PI_F * 5.9604644775390625e-08f), PI_F);
-                yaw = pi_to_pi(yaw);
-                uint32_t *rec = a.scen_out + plane * SC_WORDS;
-                *reinterpret_cast<uint4 *>(rec) = make_uint4(__float_as_uint(fmul(static_cast<float>(si), RES)),
-                                                            __float_as_uint(fmul(static_cast<float>(sj), RES)), __float_as_uint(yaw),
-                                                            __float_as_uint(fmul(static_cast<float>(gi), RES)));
-                *reinterpret_cast<uint4 *>(rec + 4) = make_uint4(__float_as_uint(fmul(static_cast<float>(gj), RES)),
-                                                                static_cast<uint32_t>(gi), static_cast<uint32_t>(gj), key);
+                sp = sample_scenario(key, G, a.goal_mode);
+                store_scenario_record(a.scen_out + plane * SC_WORDS, sp, key);
             }
-            si = __shfl_sync(FULL, si, 0); sj = __shfl_sync(FULL, sj, 0);
-            gi = __shfl_sync(FULL, gi, 0); gj = __shfl_sync(FULL, gj, 0);
-            const int bs = a.block_shift;
-            const int bw = 1 << bs;                          // obstacle block width in cells
+            sp.si = __shfl_sync(FULL, sp.si, 0); sp.sj = __shfl_sync(FULL, sp.sj, 0);
+            sp.gi = __shfl_sync(FULL, sp.gi, 0); sp.gj = __shfl_sync(FULL, sp.gj, 0);
+            gi = sp.gi; gj = sp.gj;
 #pragma unroll
-            for (int r = 0; r < RPL; ++r) {
-                const int R = lane * RPL + r;
-                const bool interior_row = R > 0 && R < G - 1;
-                const bool near_s = abs(R - si) <= 2, near_g = abs(R - gi) <= 2;
+            for (int r = 0; r < RPL; ++r)
 #pragma unroll
-                for (int w = 0; w < WPR; ++w) {
-                    const int c0 = 32 * w;
-                    uint32_t occ = 0;
-                    if (bw >= 32) {
-                        const uint32_t blk = (static_cast<uint32_t>(R >> bs) << 16) | static_cast<uint32_t>(c0 >> bs);
-                        occ = mix32(key + blk * 0x9E3779B1u) < a.p_thresh ? 0xFFFFFFFFu : 0u;
-                    } else {
-                        const uint32_t bmask = bw >= 32 ? 0xFFFFFFFFu : ((1u << bw) - 1u);
-                        for (int c = 0; c < 32; c += bw) {
-                            const uint32_t blk = (static_cast<uint32_t>(R >> bs) << 16) | static_cast<uint32_t>((c0 + c) >> bs);
-                            if (mix32(key + blk * 0x9E3779B1u) < a.p_thresh) occ |= bmask << c;
-                        }
-                    }
-                    uint32_t fr = ~occ;
-                    if (near_s) fr |= col_range_mask(sj - 2, sj + 2, c0);          // cleared 5x5 around the start
-                    if (near_g) fr |= col_range_mask(gj - 2, gj + 2, c0);          // ... and around the goal
-                    fr &= col_range_mask(1, G - 2, c0);                             // border columns / padding
-                    FR[r][w] = interior_row ? fr : 0u;                              // border rows / padding rows
-                }
-            }
+                for (int w = 0; w < WPR; ++w)
+                    FR[r][w] = scenario_free_word(key, lane * RPL + r, 32 * w, G, a.block_shift, a.p_thresh, sp);
         } else {
             if (a.slot_mode) {
                 plane = static_cast<size_t>((a.episode ? a.episode[item] : a.episode_const) % a.S) * a.N + env;
@@ -592,15 +538,21 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
 
 }  // namespace
 
-bool flow_field_supported(int G) { return G >= 16 && G <= 128 && (G % 4) == 0; }
+bool flow_field_large_supported(int G);
+int flow_field_large_max_grid(int G);
+cudaError_t launch_flow_field_large(const FlowArgs &a, int grid, cudaStream_t st);
+
+bool flow_field_supported(int G) { return (G >= 16 && G <= 128 && (G % 4) == 0) || flow_field_large_supported(G); }
 
 size_t flow_field_scratch_words(int G) {
+    if (G > 128) return 0;   // the large-map kernel keeps everything in shared memory and the cost plane
     // spill planes for cost bits 8..15 of the padded grid ((G+31)/32*32)^2
     const int wpr = (G + 31) / 32;
     return static_cast<size_t>(8) * 32 * wpr * wpr;
 }
 
 int flow_field_max_grid(int G) {
+    if (G > 128) return flow_field_large_max_grid(G);
     const int wpr = (G + 31) / 32;
     const int smem = NPL * 32 * wpr * wpr * 4 + 1024;
     int per_sm = (227 * 1024) / smem;
@@ -610,6 +562,7 @@ int flow_field_max_grid(int G) {
 
 cudaError_t launch_flow_field(const FlowArgs &a, int grid, cudaStream_t st) {
     if (grid <= 0) return cudaSuccess;
+    if (a.G > 128) return launch_flow_field_large(a, grid, st);
     const int wpr = (a.G + 31) / 32;
     if (a.generate) {
         switch (wpr) {

@@ -8,12 +8,6 @@
 
 namespace ffmp {
 
-__device__ __forceinline__ void cell_of(uint32_t u, int G, int &i, int &j) {
-    const uint32_t span = static_cast<uint32_t>(G - 6);
-    i = 3 + static_cast<int>((u & 0xFFFFu) % span);
-    j = 3 + static_cast<int>((u >> 16) % span);
-}
-
 __global__ void __launch_bounds__(256) scenario_kernel(ScenarioArgs a) {
     __shared__ int s_cells[4];
     __shared__ uint32_t s_key;
@@ -28,31 +22,9 @@ __global__ void __launch_bounds__(256) scenario_kernel(ScenarioArgs a) {
         const size_t plane = a.slot_mode ? static_cast<size_t>(episode % a.S) * a.N + env : static_cast<size_t>(item);
         if (threadIdx.x == 0) {
             const uint32_t key = scenario_key(a.seed, gid, episode);
-            int si, sj, gi, gj;
-            if (a.goal_mode == 0) {
-                cell_of(draw(key, S_START, 0), G, si, sj);
-                for (uint32_t t = 0; t < 64; ++t) {
-                    cell_of(draw(key, S_GOAL, t), G, gi, gj);
-                    if ((gi - si) * (gi - si) + (gj - sj) * (gj - sj) >= 400) break;
-                }
-            } else {
-                gi = G - 8; gj = G - 8;
-                for (uint32_t t = 0; t < 64; ++t) {
-                    cell_of(draw(key, S_START, t), G, si, sj);
-                    if ((gi - si) * (gi - si) + (gj - sj) * (gj - sj) >= 400) break;
-                }
-            }
-            float yaw = fsub(fmul(static_cast<float>(draw(key, S_YAW, 0) >> 8), TWO_PI_F * 5.9604644775390625e-08f), PI_F);
-            yaw = pi_to_pi(yaw);
-            uint32_t *rec = a.scen + plane * SC_WORDS;
-            rec[SC_X0] = __float_as_uint(fmul(static_cast<float>(si), RES));
-            rec[SC_Y0] = __float_as_uint(fmul(static_cast<float>(sj), RES));
-            rec[SC_YAW0] = __float_as_uint(yaw);
-            rec[SC_GX] = __float_as_uint(fmul(static_cast<float>(gi), RES));
-            rec[SC_GY] = __float_as_uint(fmul(static_cast<float>(gj), RES));
-            rec[SC_GI] = static_cast<uint32_t>(gi);
-            rec[SC_GJ] = static_cast<uint32_t>(gj);
-            rec[SC_KEY] = key;
+            const ScenarioParams sp = sample_scenario(key, G, a.goal_mode);
+            store_scenario_record(a.scen + plane * SC_WORDS, sp, key);
+            const int si = sp.si, sj = sp.sj, gi = sp.gi, gj = sp.gj;
             s_cells[0] = si; s_cells[1] = sj; s_cells[2] = gi; s_cells[3] = gj;
             s_key = key;
         }

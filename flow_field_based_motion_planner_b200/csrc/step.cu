@@ -422,11 +422,15 @@ __global__ void __launch_bounds__(128) rewarder_kernel(RewarderArgs a) {
 
 }  // namespace
 
-cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t st) {
+cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t st, cudaEvent_t between) {
     if (a.N <= 0) return cudaSuccess;
     dynamics_kernel<<<(a.N + 127) / 128, 128, 0, st>>>(a);
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return ce;
+    if (between) {   // profiling mode: a timing event between the two kernels
+        ce = cudaEventRecord(between, st);
+        if (ce != cudaSuccess) return ce;
+    }
     // programmatic dependent launch: the observe CTAs become resident while dynamics_kernel drains
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(a.N));

@@ -48,7 +48,8 @@ def flow_field(occ, goal_cells, want_cost=True):
     occ = occ.contiguous()
     n, G = occ.shape[0], occ.shape[1]
     goals = goal_cells.to(device=occ.device, dtype=torch.int32).contiguous()
-    cost = torch.empty((n, G, G), dtype=torch.int32, device=occ.device) if want_cost else None
+    need_cost = want_cost or G > 128          # the large-map kernel computes directions from the cost plane
+    cost = torch.empty((n, G, G), dtype=torch.int32, device=occ.device) if need_cost else None
     flow = torch.empty((n, G, G), dtype=torch.uint8, device=occ.device)
     if n == 0:
         return cost, flow
@@ -58,10 +59,10 @@ def flow_field(occ, goal_cells, want_cost=True):
     ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=occ.device)
     with torch.cuda.device(occ.device):
         native.check(L.ffmp_op_flow_field(dev, n, G, C.c_void_p(occ.data_ptr()), C.c_void_p(goals.data_ptr()),
-                                          C.c_void_p(cost.data_ptr()) if want_cost else None,
+                                          C.c_void_p(cost.data_ptr()) if need_cost else None,
                                           C.c_void_p(flow.data_ptr()), C.c_void_p(ws.data_ptr()), _stream(occ.device)),
                      "ffmp_op_flow_field")
-    return cost, flow
+    return (cost if want_cost else None), flow
 
 
 def flow_dir(flow):

@@ -221,6 +221,14 @@ class FFMPVectorEnv:
         with torch.cuda.device(self.device):
             native.check(self._L.ffmp_join(self._h, self._stream()), "ffmp_join")
 
+    def kernel_timing(self, enable: bool):
+        """enable=True: start per-kernel CUDA-event timing of the next <=256 ticks; enable=False: stop and return
+        {'dynamics_ms', 'observe_ms', 'ticks'} (averages per launch)."""
+        d, o, n = C.c_float(), C.c_float(), C.c_int32()
+        with torch.cuda.device(self.device):
+            native.check(self._L.ffmp_timing(self._h, 1 if enable else 0, C.byref(d), C.byref(o), C.byref(n)), "ffmp_timing")
+        return None if enable else {"dynamics_ms": d.value, "observe_ms": o.value, "ticks": n.value}
+
     def error_word(self) -> int:
         w = C.c_uint32()
         with torch.cuda.device(self.device):

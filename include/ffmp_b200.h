@@ -124,6 +124,11 @@ int ffmp_rollout(ffmp_handle *h, const int64_t *actions_dev, int32_t T, void *st
 int ffmp_step_host(ffmp_handle *h, const int64_t *actions_host, float *reward_host, uint8_t *done_host,
                    uint8_t *flags_host, float *rel_goal_host, float *velocity_host, void *stream);
 
+/* Per-kernel device timing of the step path (CUDA events on the caller's stream around dynamics_kernel and
+ * the observe kernel).  enable != 0: start recording the next (at most 256) ticks.  enable == 0: stop,
+ * synchronise the recorded events and return the averages in milliseconds.                          */
+int ffmp_timing(ffmp_handle *h, int32_t enable, float *dynamics_ms, float *observe_ms, int32_t *ticks);
+
 /* Index of the newest frame slot p (1 <= p <= K-1): the observation is frames[:, p-1 : p+1]. */
 int ffmp_obs_slot(const ffmp_handle *h, int32_t *newest_slot);
 

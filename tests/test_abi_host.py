@@ -46,7 +46,7 @@ def test_cfg_validation_without_gpu():
     assert sz.flow == 3 * 8 * 128 * 128 and sz.cost == 4 * sz.flow and sz.frames == 8 * 8 * 100 * 100
     assert sz.state == 8 * 64 and sz.scen == 3 * 8 * 32 and sz.workspace > 0
     for key, bad in [("abi_version", 2), ("num_envs", 0), ("grid", 130), ("grid", 8), ("window", 102), ("ring", 1),
-                     ("slots", 1), ("max_steps", 0), ("goal_mode", 2), ("dt", 0.0), ("grid", 512)]:
+                     ("slots", 1), ("max_steps", 0), ("goal_mode", 2), ("dt", 0.0), ("grid", 1024), ("grid", 144)]:
         rc = L.ffmp_query_sizes(C.byref(native.Cfg(**{**good, key: bad})), C.byref(sz))
         assert rc < 0, key
         assert len(L.ffmp_last_error()) > 0

@@ -83,6 +83,31 @@ def test_flow_field_generated_maps_bit_exact(ffmp, cuda_device, G, bs, p):
         assert np.array_equal(flow[k], ef), (k, "flow")
 
 
+@pytest.mark.parametrize("G", [160, 256, 512])
+def test_flow_field_large_maps_bit_exact(ffmp, cuda_device, G):
+    """Large-map path (one CTA per grid): special maps incl. the deep serpentine, and BASELINE config 4's
+    shape (512x512, dense i.i.d. obstacles p=0.30)."""
+    cases = special_cases(G)
+    if G == 512:
+        cases = [c for c in cases if c[0] in ("open", "serpentine", "rooms0", "noise0.35", "sealed_pocket", "goal_blocked")]
+    for k in range(4):
+        o, _, _, cells = oracle.scenario(77, k, 0, G, p_occ=0.30, block_shift=0)
+        cases.append((f"config4_{k}", o, (cells[2], cells[3])))
+    cost, flow = run_flow(ffmp, cuda_device, [c[1] for c in cases], [c[2] for c in cases])
+    for k, (name, occ, goal) in enumerate(cases):
+        ec, ed, ef = oracle.flow_field(occ, goal[0], goal[1])
+        assert np.array_equal(cost[k], ec), (G, name, "cost", int((cost[k] != ec).sum()))
+        assert np.array_equal(flow[k], ef), (G, name, "flow", int((flow[k] != ef).sum()))
+    _, flow2 = run_flow(ffmp, cuda_device, [cases[0][1]], [cases[0][2]], want_cost=False)
+    assert np.array_equal(flow2[0], oracle.flow_field(cases[0][1], *cases[0][2])[2])
+
+
+def test_rollout_large_map_config4_shape(ffmp):
+    """config 4 per-env shape: 512x512 grid with dense i.i.d. obstacles (p=0.30), W=100."""
+    rollout_parity(ffmp, 6, 120, seed=4, grid=512, window=100, p_occ=0.30, block_shift=0, slots=3, check_every=60)
+    rollout_parity(ffmp, 8, 150, seed=5, grid=256, window=100, check_every=75)
+
+
 def test_flow_field_without_cost_output(ffmp, cuda_device):
     occs, goals = [], []
     for k in range(8):
@@ -277,7 +302,7 @@ def test_invalid_actions_and_errors(ffmp, cuda_device):
         env.step(torch.zeros(5, dtype=torch.int64, device=cuda_device))
     env.close()
     with pytest.raises(ffmp.native.NativeError):
-        ffmp.FFMPVectorEnv(4, grid=512)                                         # unsupported in this build
+        ffmp.FFMPVectorEnv(4, grid=1024)                                        # unsupported in this build
     with pytest.raises(ffmp.native.NativeError):
         ffmp.FFMPVectorEnv(4, window=50)
 
