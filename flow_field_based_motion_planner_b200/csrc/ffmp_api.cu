@@ -1,6 +1,7 @@
 // ffmp_api.cu — the C-ABI of libffmp_b200.so (include/ffmp_b200.h): handle, buffer binding, stream /
 // event plumbing for the background scenario regeneration, and the stateless operators.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -117,6 +118,7 @@ struct ffmp_handle {
     int rg_grid = 0;                // background regeneration grid (few items per tick)
     CUtensorMap tmap;               // flow planes as a 3-D u8 tensor for the TMA observe kernel
     bool use_tma = false;
+    bool fused = true;              // one kernel per tick (env FFMP_STEP_FUSED=0 selects dynamics + observe kernels)
     // optional per-kernel timing (ffmp_timing): event triplets [before dynamics, between, after observe]
     static constexpr int TIMING_RING = 256;
     bool timing = false;
@@ -187,7 +189,7 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
         CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st, t[1]));
         CK(cudaEventRecord(t[2], st));
     } else {
-        CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st));
+        CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st, nullptr, h->fused));
     }
     CK(cudaEventRecord(h->ev_step[l], st));
     CK(cudaStreamWaitEvent(h->side[l], h->ev_step[l], 0));
@@ -234,6 +236,7 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
     ffmp_handle *h = new (std::nothrow) ffmp_handle();
     if (!h) return fail(FFMP_ERR_ARG, "out of host memory");
     h->cfg = *cfg;
+    if (const char *f = std::getenv("FFMP_STEP_FUSED")) h->fused = std::atoi(f) != 0;
     h->ws = workspace_layout(cfg);
     h->nlist = cfg->slots - 1;
     std::memset(&h->b, 0, sizeof(h->b));
@@ -343,7 +346,7 @@ int ffmp_reset(ffmp_handle *h, const uint8_t *mask_dev, void *stream) {
     ffmp::StepArgs a = step_args(h);
     a.mode = 2; a.slot_new = 1; a.write_older = 1;
     a.regen_env = h->list_env(0); a.regen_episode = h->list_episode(0); a.regen_count = h->list_count(0);
-    CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st));
+    CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st, nullptr, h->fused));
     h->ready = true;
     return FFMP_OK;
 }

@@ -48,9 +48,12 @@ __device__ __forceinline__ ColPlan make_plan(int G, int j0) {
     return p;
 }
 
-__global__ void __launch_bounds__(128) dynamics_kernel(StepArgs a) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= a.N) return;
+// The per-env scalar step (SPEC.md §7).  WARP = false: one thread per env.  WARP = true: a whole warp runs it
+// redundantly for one env (lanes 0..20 take one footprint cell each, lane 0 does the writes); every lane
+// returns the same crop order.  o0 = (ci, cj, pi, pj), o1 = (plane, flags: bit0 active, bit1 two frames).
+template <bool WARP>
+__device__ __forceinline__ void dynamics_env(const StepArgs &a, int e, int lane, uint4 &o0, uint2 &o1) {
+    const bool lead = !WARP || lane == 0;
     const int G = a.G;
     const size_t cells = static_cast<size_t>(G) * G;
     uint32_t *st = a.state + static_cast<size_t>(e) * ST_WORDS;
@@ -69,7 +72,7 @@ __global__ void __launch_bounds__(128) dynamics_kernel(StepArgs a) {
         long long act = a.actions[e];
         if (act < 0 || act >= 28) {
             act = 3;
-            atomicOr(a.error_word, 1u);
+            if (lead) atomicOr(a.error_word, 1u);
         }
         float v, w, s, c;
         action_lookup(static_cast<int>(act), v, w);
@@ -79,10 +82,17 @@ __global__ void __launch_bounds__(128) dynamics_kernel(StepArgs a) {
         const float nyaw = pi_to_pi(fadd(yaw, fmul(w, a.dt)));
         ci = robot_cell(nx);
         cj = robot_cell(ny);
-        // footprint: 21 independent byte loads in flight
         const uint8_t *img = a.flow + (static_cast<size_t>(episode % a.S) * a.N + e) * cells;
-        bool col = false;
-        if (ci >= 2 && cj >= 2 && ci < G - 2 && cj < G - 2) {
+        bool col;
+        if (WARP) {
+            bool hit = false;
+            if (lane < 21) {
+                const int i = ci + FOOT_DI[lane], j = cj + FOOT_DJ[lane];
+                hit = static_cast<unsigned>(i) >= static_cast<unsigned>(G) || static_cast<unsigned>(j) >= static_cast<unsigned>(G);
+                if (!hit) hit = __ldg(img + static_cast<size_t>(i) * G + j) == 255;
+            }
+            col = __ballot_sync(FULL, hit) != 0;
+        } else if (ci >= 2 && cj >= 2 && ci < G - 2 && cj < G - 2) {
             // all 21 loads are issued before the first use (one memory round trip, not 21)
             const uint8_t *centre = img + static_cast<size_t>(ci) * G + cj;
             uint32_t cell[21];
@@ -106,23 +116,26 @@ __global__ void __launch_bounds__(128) dynamics_kernel(StepArgs a) {
         const bool trunc = steps == a.max_steps;
         const bool done = col || goal || trunc;
         ep_return = fadd(ep_return, r);
-        a.reward[e] = r;
-        a.done[e] = done ? 1 : 0;
-        a.flags[e] = static_cast<uint8_t>((col ? 1 : 0) | (goal ? 2 : 0) | (trunc ? 4 : 0));
-        *reinterpret_cast<float2 *>(a.term_rel_goal + 2 * e) = make_float2(d, bearing);
-        *reinterpret_cast<float2 *>(a.term_velocity + 2 * e) = make_float2(vl, va);
+        if (lead) {
+            a.reward[e] = r;
+            a.done[e] = done ? 1 : 0;
+            a.flags[e] = static_cast<uint8_t>((col ? 1 : 0) | (goal ? 2 : 0) | (trunc ? 4 : 0));
+            *reinterpret_cast<float2 *>(a.term_rel_goal + 2 * e) = make_float2(d, bearing);
+            *reinterpret_cast<float2 *>(a.term_velocity + 2 * e) = make_float2(vl, va);
+        }
         if (done) {
-            a.fin_return[e] = ep_return;
-            a.fin_length[e] = steps;
+            if (lead) { a.fin_return[e] = ep_return; a.fin_length[e] = steps; }
             begin = true;
         } else {
             pi = robot_cell(x);
             pj = robot_cell(y);
-            st[ST_X] = __float_as_uint(nx); st[ST_Y] = __float_as_uint(ny); st[ST_YAW] = __float_as_uint(nyaw);
-            st[ST_RETURN] = __float_as_uint(ep_return);
-            st[ST_STEPS] = static_cast<uint32_t>(steps);
-            *reinterpret_cast<float2 *>(a.rel_goal + 2 * e) = make_float2(d, bearing);
-            *reinterpret_cast<float2 *>(a.velocity + 2 * e) = make_float2(vl, va);
+            if (lead) {
+                st[ST_X] = __float_as_uint(nx); st[ST_Y] = __float_as_uint(ny); st[ST_YAW] = __float_as_uint(nyaw);
+                st[ST_RETURN] = __float_as_uint(ep_return);
+                st[ST_STEPS] = static_cast<uint32_t>(steps);
+                *reinterpret_cast<float2 *>(a.rel_goal + 2 * e) = make_float2(d, bearing);
+                *reinterpret_cast<float2 *>(a.velocity + 2 * e) = make_float2(vl, va);
+            }
         }
     } else if (a.mode == 1) {
         begin = a.mask[e] != 0;
@@ -134,10 +147,12 @@ __global__ void __launch_bounds__(128) dynamics_kernel(StepArgs a) {
     if (begin) {
         if (a.mode != 2) {
             episode += 1;
-            // the slot of the finished episode is refilled with episode + S - 1
-            const uint32_t idx = atomicAdd(a.regen_count, 1u);
-            a.regen_env[idx] = static_cast<uint32_t>(e);
-            a.regen_episode[idx] = episode + static_cast<uint32_t>(a.S) - 1u;
+            if (lead) {
+                // the slot of the finished episode is refilled with episode + S - 1
+                const uint32_t idx = atomicAdd(a.regen_count, 1u);
+                a.regen_env[idx] = static_cast<uint32_t>(e);
+                a.regen_episode[idx] = episode + static_cast<uint32_t>(a.S) - 1u;
+            }
         }
         const uint32_t *rec = a.scen + (static_cast<size_t>(episode % a.S) * a.N + e) * SC_WORDS;
         const uint4 r0 = *reinterpret_cast<const uint4 *>(rec);
@@ -148,18 +163,29 @@ __global__ void __launch_bounds__(128) dynamics_kernel(StepArgs a) {
         const float bearing = pi_to_pi(fsub(atan2_spec(dy, dx), yaw));
         ci = pi = robot_cell(x);
         cj = pj = robot_cell(y);
-        *reinterpret_cast<uint4 *>(st) = make_uint4(__float_as_uint(x), __float_as_uint(y), __float_as_uint(yaw), __float_as_uint(ngx));
-        *reinterpret_cast<uint4 *>(st + 4) = make_uint4(__float_as_uint(ngy), __float_as_uint(d), __float_as_uint(0.0f), 0u);
-        st[ST_EPISODE] = episode;
-        *reinterpret_cast<float2 *>(a.rel_goal + 2 * e) = make_float2(d, bearing);
-        *reinterpret_cast<float2 *>(a.velocity + 2 * e) = make_float2(0.0f, 0.0f);
-        if (a.mode == 2) { a.reward[e] = 0.0f; a.done[e] = 0; a.flags[e] = 0; }
+        if (lead) {
+            *reinterpret_cast<uint4 *>(st) = make_uint4(__float_as_uint(x), __float_as_uint(y), __float_as_uint(yaw), __float_as_uint(ngx));
+            *reinterpret_cast<uint4 *>(st + 4) = make_uint4(__float_as_uint(ngy), __float_as_uint(d), __float_as_uint(0.0f), 0u);
+            st[ST_EPISODE] = episode;
+            *reinterpret_cast<float2 *>(a.rel_goal + 2 * e) = make_float2(d, bearing);
+            *reinterpret_cast<float2 *>(a.velocity + 2 * e) = make_float2(0.0f, 0.0f);
+            if (a.mode == 2) { a.reward[e] = 0.0f; a.done[e] = 0; a.flags[e] = 0; }
+        }
     }
+    o0 = make_uint4(static_cast<uint32_t>(ci), static_cast<uint32_t>(cj), static_cast<uint32_t>(pi), static_cast<uint32_t>(pj));
+    o1 = make_uint2((episode % a.S) * static_cast<uint32_t>(a.N) + static_cast<uint32_t>(e),
+                    (active ? 1u : 0u) | ((begin || a.write_older) ? 2u : 0u));
+}
+
+__global__ void __launch_bounds__(128) dynamics_kernel(StepArgs a) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.N) return;
+    uint4 o0;
+    uint2 o1;
+    dynamics_env<false>(a, e, 0, o0, o1);
     uint32_t *ob = a.obs_order + static_cast<size_t>(e) * OB_WORDS;
-    *reinterpret_cast<uint4 *>(ob) = make_uint4(static_cast<uint32_t>(ci), static_cast<uint32_t>(cj),
-                                               static_cast<uint32_t>(pi), static_cast<uint32_t>(pj));
-    *reinterpret_cast<uint2 *>(ob + 4) = make_uint2((episode % a.S) * static_cast<uint32_t>(a.N) + static_cast<uint32_t>(e),
-                                                   (active ? 1u : 0u) | ((begin || a.write_older) ? 2u : 0u));
+    *reinterpret_cast<uint4 *>(ob) = o0;
+    *reinterpret_cast<uint2 *>(ob + 4) = o1;
 }
 
 constexpr int ROWS_IN_FLIGHT = 8;
@@ -301,6 +327,10 @@ __device__ __forceinline__ void drain_tile(const uint32_t *__restrict__ tile32, 
     }
 }
 
+// FUSED = true: warp 0 runs the scalar step of this env itself (dynamics_env<true>) before issuing the TMA, so a
+// tick is ONE kernel; the other warps sleep on the barrier meanwhile and other CTAs of the SM cover the latency.
+// FUSED = false: the crop order comes from dynamics_kernel (programmatic dependent launch).
+template <bool FUSED>
 __global__ void __launch_bounds__(128) observe_tma_kernel(const __grid_constant__ CUtensorMap tmap, StepArgs a) {
     extern __shared__ __align__(128) uint8_t tile[];
     __shared__ __align__(8) uint64_t mbar;
@@ -316,11 +346,24 @@ __global__ void __launch_bounds__(128) observe_tma_kernel(const __grid_constant_
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    const uint32_t *ob = a.obs_order + static_cast<size_t>(e) * OB_WORDS;
-    const uint4 o0 = *reinterpret_cast<const uint4 *>(ob);
-    const uint2 o1 = *reinterpret_cast<const uint2 *>(ob + 4);
+    uint4 o0;
+    uint2 o1;
+    if (FUSED) {
+        __shared__ uint4 s_o0;
+        __shared__ uint2 s_o1;
+        if (warp == 0) {
+            dynamics_env<true>(a, e, lane, o0, o1);
+            if (lane == 0) { s_o0 = o0; s_o1 = o1; }
+        }
+        __syncthreads();
+        o0 = s_o0; o1 = s_o1;
+    } else {
+        __syncthreads();
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        const uint32_t *ob = a.obs_order + static_cast<size_t>(e) * OB_WORDS;
+        o0 = *reinterpret_cast<const uint4 *>(ob);
+        o1 = *reinterpret_cast<const uint2 *>(ob + 4);
+    }
     if (!(o1.y & 1u)) return;
     const bool two = (o1.y & 2u) != 0;
     const int ci = static_cast<int>(o0.x), cj = static_cast<int>(o0.y), pi = static_cast<int>(o0.z), pj = static_cast<int>(o0.w);
@@ -388,6 +431,224 @@ __global__ void __launch_bounds__(128) observe_tma_kernel(const __grid_constant_
     }
 }
 
+// ---- tick_tma_kernel: the whole env step in ONE kernel, latency-optimised --------------------------------
+// One CTA per env.  Warp 0: state + action -> kinematics -> robot cell, then IMMEDIATELY issues the TMA for the
+// window around the new cell (speculating that the episode continues) and overlaps the relative-goal / velocity
+// math with the copy.  When the tile has landed the 21 footprint cells are read from SHARED memory (they sit
+// at the centre of the window), so the collision test costs no extra global round trip.  Only if the episode
+// ended (rare) a second TMA fetches the first window of the next scenario.  All four warps then stream the
+// frame to the ring.  Critical path per CTA: one state load, one TMA, one drain.
+struct TickShared {
+    int go, two, ci, cj, pi, pj, parity;
+    unsigned int plane;
+};
+
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(128) tick_tma_kernel(const __grid_constant__ CUtensorMap tmap, StepArgs a) {
+    extern __shared__ __align__(128) uint8_t tile[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ TickShared sh;
+    const int e = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int G = a.G, W = a.W;
+    const int wpr = W >> 2;
+    const int tile_w = (W + 15 + 15) & ~15;
+    const int tile_wpr = tile_w >> 2;
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&mbar));
+    const uint32_t tile_s = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
+    const uint32_t bytes = static_cast<uint32_t>(tile_w * W);
+    const int half = W >> 1;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        uint32_t *st = a.state + static_cast<size_t>(e) * ST_WORDS;
+        const uint4 s0 = *reinterpret_cast<const uint4 *>(st);        // x y yaw gx
+        const uint4 s1 = *reinterpret_cast<const uint4 *>(st + 4);    // gy d_first return steps
+        float x = __uint_as_float(s0.x), y = __uint_as_float(s0.y), yaw = __uint_as_float(s0.z);
+        const float gx = __uint_as_float(s0.w), gy = __uint_as_float(s1.x);
+        const float d_first = __uint_as_float(s1.y);
+        float ep_return = __uint_as_float(s1.z);
+        int steps = static_cast<int>(s1.w);
+        uint32_t episode = st[ST_EPISODE];
+        bool begin = false, active = true;
+        int ci = 0, cj = 0, pi = 0, pj = 0;
+        int parity = 0;
+
+        if (a.mode == 0) {
+            long long act = a.actions[e];
+            if (act < 0 || act >= 28) {
+                act = 3;
+                if (lane == 0) atomicOr(a.error_word, 1u);
+            }
+            float v, w, s, c;
+            action_lookup(static_cast<int>(act), v, w);
+            sincos_spec(yaw, s, c);
+            const float nx = fadd(x, fmul(fmul(v, c), a.dt));
+            const float ny = fadd(y, fmul(fmul(v, s), a.dt));
+            const float nyaw = pi_to_pi(fadd(yaw, fmul(w, a.dt)));
+            ci = robot_cell(nx);
+            cj = robot_cell(ny);
+            const int i0 = ci - half, j0 = cj - half;
+            if (lane == 0) {   // speculative window fetch: the episode usually continues
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                tma_window(tile_s, &tmap, j0 & ~15, i0, static_cast<int>((episode % a.S) * a.N + e), bar);
+            }
+            // math that does not depend on the map overlaps the copy
+            const float dx = fsub(gx, nx), dy = fsub(gy, ny);
+            const float d = dist_spec(dx, dy);
+            const float bearing = pi_to_pi(fsub(atan2_spec(dy, dx), nyaw));
+            const float vl = dist_spec(fsub(nx, x), fsub(ny, y));
+            const float va = pi_to_pi(fsub(nyaw, yaw));
+            const bool goal = d < 0.5f;
+            mbar_wait_parity(bar, 0);
+            bool hit = false;
+            if (lane < 21) {
+                const int di = FOOT_DI[lane], dj = FOOT_DJ[lane];
+                const int i = ci + di, j = cj + dj;
+                hit = static_cast<unsigned>(i) >= static_cast<unsigned>(G) || static_cast<unsigned>(j) >= static_cast<unsigned>(G);
+                if (!hit) hit = tile[(half + di) * tile_w + (j0 & 15) + half + dj] == 255;
+            }
+            const bool col = __ballot_sync(FULL, hit) != 0;
+            const float r = fadd(fadd(goal ? 1.0f : fmul(0.05f, fsub(d_first, d)), col ? -1.0f : 0.0f), -0.05f);
+            steps += 1;
+            const bool trunc = steps == a.max_steps;
+            const bool done = col || goal || trunc;
+            ep_return = fadd(ep_return, r);
+            if (lane == 0) {
+                a.reward[e] = r;
+                a.done[e] = done ? 1 : 0;
+                a.flags[e] = static_cast<uint8_t>((col ? 1 : 0) | (goal ? 2 : 0) | (trunc ? 4 : 0));
+                *reinterpret_cast<float2 *>(a.term_rel_goal + 2 * e) = make_float2(d, bearing);
+                *reinterpret_cast<float2 *>(a.term_velocity + 2 * e) = make_float2(vl, va);
+            }
+            if (done) {
+                if (lane == 0) { a.fin_return[e] = ep_return; a.fin_length[e] = steps; }
+                begin = true;
+                parity = 1;   // the window of the next scenario arrives in the barrier's second phase
+            } else {
+                pi = robot_cell(x);
+                pj = robot_cell(y);
+                if (lane == 0) {
+                    st[ST_X] = __float_as_uint(nx); st[ST_Y] = __float_as_uint(ny); st[ST_YAW] = __float_as_uint(nyaw);
+                    st[ST_RETURN] = __float_as_uint(ep_return);
+                    st[ST_STEPS] = static_cast<uint32_t>(steps);
+                    *reinterpret_cast<float2 *>(a.rel_goal + 2 * e) = make_float2(d, bearing);
+                    *reinterpret_cast<float2 *>(a.velocity + 2 * e) = make_float2(vl, va);
+                }
+            }
+        } else if (a.mode == 1) {
+            begin = a.mask[e] != 0;
+            active = begin;
+        } else {
+            begin = true;
+        }
+
+        if (begin) {
+            if (a.mode != 2) {
+                episode += 1;
+                if (lane == 0) {
+                    const uint32_t idx = atomicAdd(a.regen_count, 1u);
+                    a.regen_env[idx] = static_cast<uint32_t>(e);
+                    a.regen_episode[idx] = episode + static_cast<uint32_t>(a.S) - 1u;
+                }
+            }
+            const uint32_t *rec = a.scen + (static_cast<size_t>(episode % a.S) * a.N + e) * SC_WORDS;
+            const uint4 r0 = *reinterpret_cast<const uint4 *>(rec);
+            x = __uint_as_float(r0.x); y = __uint_as_float(r0.y); yaw = __uint_as_float(r0.z);
+            const float ngx = __uint_as_float(r0.w), ngy = __uint_as_float(rec[SC_GY]);
+            ci = pi = robot_cell(x);
+            cj = pj = robot_cell(y);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // footprint reads of `tile` precede the overwrite
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                tma_window(tile_s, &tmap, (cj - half) & ~15, ci - half, static_cast<int>((episode % a.S) * a.N + e), bar);
+            }
+            const float dx = fsub(ngx, x), dy = fsub(ngy, y);
+            const float d = dist_spec(dx, dy);
+            const float bearing = pi_to_pi(fsub(atan2_spec(dy, dx), yaw));
+            if (lane == 0) {
+                *reinterpret_cast<uint4 *>(st) = make_uint4(__float_as_uint(x), __float_as_uint(y), __float_as_uint(yaw), __float_as_uint(ngx));
+                *reinterpret_cast<uint4 *>(st + 4) = make_uint4(__float_as_uint(ngy), __float_as_uint(d), __float_as_uint(0.0f), 0u);
+                st[ST_EPISODE] = episode;
+                *reinterpret_cast<float2 *>(a.rel_goal + 2 * e) = make_float2(d, bearing);
+                *reinterpret_cast<float2 *>(a.velocity + 2 * e) = make_float2(0.0f, 0.0f);
+                if (a.mode == 2) { a.reward[e] = 0.0f; a.done[e] = 0; a.flags[e] = 0; }
+            }
+        }
+        if (lane == 0) {
+            sh.go = active ? 1 : 0;
+            sh.two = (begin || a.write_older) ? 1 : 0;
+            sh.ci = ci; sh.cj = cj; sh.pi = pi; sh.pj = pj;
+            sh.parity = parity;
+            sh.plane = (episode % a.S) * static_cast<uint32_t>(a.N) + static_cast<uint32_t>(e);
+        }
+    }
+    __syncthreads();
+    if (!sh.go) return;
+    const bool two = sh.two != 0;
+    const int ci = sh.ci, cj = sh.cj, pi = sh.pi, pj = sh.pj;
+    const bool same = pi == ci && pj == cj;
+    const int i0 = ci - half, j0 = cj - half;
+    uint32_t parity = static_cast<uint32_t>(sh.parity);
+    mbar_wait_parity(bar, parity);
+
+    uint32_t *f_new = reinterpret_cast<uint32_t *>(a.frames + (static_cast<size_t>(e) * a.K + a.slot_new) * W * W);
+    uint32_t *f_old = f_new - (W * W >> 2);
+    int rpi = 1, sub = 0, wl = lane;
+    if (wpr <= 32) { rpi = 32 / wpr; sub = lane / wpr; wl = lane - sub * wpr; }
+    auto colmask = [&](int jbase, int w) {
+        uint32_t om = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (static_cast<unsigned>(jbase + 4 * w + c) >= static_cast<unsigned>(G)) om |= 0xFFu << (8 * c);
+        return om;
+    };
+    const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
+    if (wpr <= 32) {
+        if (sub < rpi) {
+            const uint32_t om = colmask(j0, wl);
+            if (two && same) drain_tile<true>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, warp * rpi + sub, 4 * rpi, wl, om, f_new, f_old);
+            else drain_tile<false>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, warp * rpi + sub, 4 * rpi, wl, om, f_new, nullptr);
+        }
+    } else {
+        for (int w2 = lane; w2 < wpr; w2 += 32)
+            drain_tile<false>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, warp, 4, w2, colmask(j0, w2), f_new, nullptr);
+        if (two && same)
+            for (int w2 = lane; w2 < wpr; w2 += 32)
+                drain_tile<false>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, warp, 4, w2, colmask(j0, w2), f_old, nullptr);
+    }
+    if (two && !same) {
+        // ring wrap of a continuing env: the older frame is the window at the previous pose
+        const int p0 = pi - half, q0 = pj - half;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            tma_window(tile_s, &tmap, q0 & ~15, p0, static_cast<int>(sh.plane), bar);
+        }
+        mbar_wait_parity(bar, parity ^ 1u);
+        if (wpr <= 32) {
+            if (sub < rpi)
+                drain_tile<false>(tile32, tile_wpr, G, W, wpr, p0, q0 & 15, warp * rpi + sub, 4 * rpi, wl, colmask(q0, wl), f_old, nullptr);
+        } else {
+            for (int w2 = lane; w2 < wpr; w2 += 32)
+                drain_tile<false>(tile32, tile_wpr, G, W, wpr, p0, q0 & 15, warp, 4, w2, colmask(q0, w2), f_old, nullptr);
+        }
+    }
+}
+
 // Batched FFMP.rewarder / rewarder2 / reward_calculator (ffmp.py:130-188): one warp per item.
 __global__ void __launch_bounds__(128) rewarder_kernel(RewarderArgs a) {
     const int item = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -422,8 +683,23 @@ __global__ void __launch_bounds__(128) rewarder_kernel(RewarderArgs a) {
 
 }  // namespace
 
-cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t st, cudaEvent_t between) {
+cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t st, cudaEvent_t between, bool fused) {
     if (a.N <= 0) return cudaSuccess;
+    const size_t smem = tmap ? static_cast<size_t>((a.W + 30) & ~15) * a.W + 16 : 0;
+    if (tmap) {
+        static size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            cudaError_t ce = cudaFuncSetAttribute(tick_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (ce == cudaSuccess)
+                ce = cudaFuncSetAttribute(observe_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (ce != cudaSuccess) return ce;
+            configured = smem;
+        }
+        if (fused && !between) {
+            tick_tma_kernel<<<a.N, 128, smem, st>>>(*tmap, a);   // the whole tick in one kernel
+            return cudaGetLastError();
+        }
+    }
     dynamics_kernel<<<(a.N + 127) / 128, 128, 0, st>>>(a);
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return ce;
@@ -441,18 +717,8 @@ cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (tmap) {
-        const size_t smem = static_cast<size_t>((a.W + 30) & ~15) * a.W + 16;   // +16: the drain reads one word past a row
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
-            ce = cudaFuncSetAttribute(observe_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-            if (ce != cudaSuccess) return ce;
-            configured = smem;
-        }
-        cfg.dynamicSmemBytes = smem;
-        return cudaLaunchKernelEx(&cfg, observe_tma_kernel, *tmap, a);
-    }
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = smem;
+    if (tmap) return cudaLaunchKernelEx(&cfg, observe_tma_kernel<false>, *tmap, a);
     return cudaLaunchKernelEx(&cfg, observe_kernel, a);
 }
 
