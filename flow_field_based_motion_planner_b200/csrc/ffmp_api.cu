@@ -119,11 +119,13 @@ struct ffmp_handle {
     CUtensorMap tmap;               // flow planes as a 3-D u8 tensor for the TMA observe kernel
     bool use_tma = false;
     bool fused = true;              // one kernel per tick (env FFMP_STEP_FUSED=0 selects dynamics + observe kernels)
-    // optional per-kernel timing (ffmp_timing): event triplets [before dynamics, between, after observe]
+    // optional per-kernel timing (ffmp_timing): events [before tick, after tick] on the caller's stream and
+    // [before regeneration, after regeneration] on the side stream of the tick
     static constexpr int TIMING_RING = 256;
     bool timing = false;
     int timing_n = 0;
-    cudaEvent_t tev[TIMING_RING][3];
+    cudaEvent_t tev[TIMING_RING][4];
+    uint64_t launches = 0;          // kernels launched by this handle (ffmp_launch_count)
 
     uint32_t *error_word() const { return reinterpret_cast<uint32_t *>(static_cast<char *>(b.workspace) + ws.error_word); }
     char *list_base(int l) const { return static_cast<char *>(b.workspace) + ws.lists + ws.list_stride * l; }
@@ -183,21 +185,22 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
         a.slot_new = h->p; a.write_older = 0;
     }
     a.regen_env = h->list_env(l); a.regen_episode = h->list_episode(l); a.regen_count = h->list_count(l);
-    if (h->timing && h->timing_n < ffmp_handle::TIMING_RING) {
-        cudaEvent_t *t = h->tev[h->timing_n++];
-        CK(cudaEventRecord(t[0], st));
-        CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st, t[1]));
-        CK(cudaEventRecord(t[2], st));
-    } else {
-        CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st, nullptr, h->fused));
-    }
+    const bool one_kernel = h->use_tma && h->fused;
+    cudaEvent_t *tev = (h->timing && h->timing_n < ffmp_handle::TIMING_RING) ? h->tev[h->timing_n++] : nullptr;
+    if (tev) CK(cudaEventRecord(tev[0], st));
+    CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st, nullptr, h->fused));
+    if (tev) CK(cudaEventRecord(tev[1], st));
+    h->launches += one_kernel ? 1 : 2;
     CK(cudaEventRecord(h->ev_step[l], st));
     CK(cudaStreamWaitEvent(h->side[l], h->ev_step[l], 0));
+    if (tev) CK(cudaEventRecord(tev[2], h->side[l]));
     ffmp::FlowArgs fa = flow_args(h);
     fa.env_idx = h->list_env(l); fa.episode = h->list_episode(l); fa.count_ptr = h->list_count(l);
     fa.ticket = h->list_ticket(l); fa.count_reset = h->list_count(l);
     fa.hi_scratch = h->hi_scratch() + (static_cast<size_t>(h->ff_grid) + static_cast<size_t>(l) * h->rg_grid) * ffmp::flow_field_scratch_words(h->cfg.grid);
     CK(ffmp::launch_flow_field(fa, h->rg_grid, h->side[l]));
+    if (tev) CK(cudaEventRecord(tev[3], h->side[l]));
+    h->launches += 1;
     CK(cudaEventRecord(h->ev_regen[l], h->side[l]));
     h->regen_pending[l] = true;
     h->step_index += 1;
@@ -316,7 +319,7 @@ int ffmp_destroy(ffmp_handle *h) {
     }
     if (h->tev[0][0])
         for (int i = 0; i < ffmp_handle::TIMING_RING; ++i)
-            for (int j = 0; j < 3; ++j) cudaEventDestroy(h->tev[i][j]);
+            for (int j = 0; j < 4; ++j) cudaEventDestroy(h->tev[i][j]);
     delete h;
     return FFMP_OK;
 }
@@ -340,6 +343,7 @@ int ffmp_reset(ffmp_handle *h, const uint8_t *mask_dev, void *stream) {
         ffmp::FlowArgs fa = flow_args(h);
         fa.count = c.num_envs; fa.episode_const = static_cast<uint32_t>(s);
         CK(ffmp::launch_flow_field(fa, h->ff_grid, st));
+        h->launches += 1;
     }
     h->p = 1;
     h->step_index = 0;
@@ -347,6 +351,7 @@ int ffmp_reset(ffmp_handle *h, const uint8_t *mask_dev, void *stream) {
     a.mode = 2; a.slot_new = 1; a.write_older = 1;
     a.regen_env = h->list_env(0); a.regen_episode = h->list_episode(0); a.regen_count = h->list_count(0);
     CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st, nullptr, h->fused));
+    h->launches += (h->use_tma && h->fused) ? 1 : 2;
     h->ready = true;
     return FFMP_OK;
 }
@@ -378,22 +383,39 @@ int ffmp_step_host(ffmp_handle *h, const int64_t *actions_host, float *reward_ho
     const size_t N = h->cfg.num_envs;
     CK(cudaMemcpyAsync(h->actions(), actions_host, N * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     if (int rc = run_tick(h, 0, h->actions(), nullptr, st)) return rc;
-    if (reward_host) CK(cudaMemcpyAsync(reward_host, h->b.reward, N * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (done_host) CK(cudaMemcpyAsync(done_host, h->b.done, N, cudaMemcpyDeviceToHost, st));
-    if (flags_host) CK(cudaMemcpyAsync(flags_host, h->b.flags, N, cudaMemcpyDeviceToHost, st));
-    if (rel_goal_host) CK(cudaMemcpyAsync(rel_goal_host, h->b.rel_goal, N * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (velocity_host) CK(cudaMemcpyAsync(velocity_host, h->b.velocity, N * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    // When the five device outputs are adjacent in memory in the order reward | rel_goal | velocity | done | flags
+    // (FFMPVectorEnv allocates them so) and the host destinations are too, ONE device-to-host copy moves them.
+    const ffmp_buffers &b = h->b;
+    const char *d0 = reinterpret_cast<const char *>(b.reward);
+    char *h0 = reinterpret_cast<char *>(reward_host);
+    const bool dev_packed = reinterpret_cast<const char *>(b.rel_goal) == d0 + 4 * N &&
+                            reinterpret_cast<const char *>(b.velocity) == d0 + 12 * N &&
+                            reinterpret_cast<const char *>(b.done) == d0 + 20 * N &&
+                            reinterpret_cast<const char *>(b.flags) == d0 + 21 * N;
+    const bool host_packed = reward_host && reinterpret_cast<char *>(rel_goal_host) == h0 + 4 * N &&
+                             reinterpret_cast<char *>(velocity_host) == h0 + 12 * N &&
+                             reinterpret_cast<char *>(done_host) == h0 + 20 * N &&
+                             reinterpret_cast<char *>(flags_host) == h0 + 21 * N;
+    if (dev_packed && host_packed) {
+        CK(cudaMemcpyAsync(h0, d0, 22 * N, cudaMemcpyDeviceToHost, st));
+    } else {
+        if (reward_host) CK(cudaMemcpyAsync(reward_host, b.reward, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (done_host) CK(cudaMemcpyAsync(done_host, b.done, N, cudaMemcpyDeviceToHost, st));
+        if (flags_host) CK(cudaMemcpyAsync(flags_host, b.flags, N, cudaMemcpyDeviceToHost, st));
+        if (rel_goal_host) CK(cudaMemcpyAsync(rel_goal_host, b.rel_goal, N * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (velocity_host) CK(cudaMemcpyAsync(velocity_host, b.velocity, N * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaStreamSynchronize(st));
     return FFMP_OK;
 }
 
-int ffmp_timing(ffmp_handle *h, int32_t enable, float *dynamics_ms, float *observe_ms, int32_t *ticks) {
+int ffmp_timing(ffmp_handle *h, int32_t enable, float *tick_ms, float *regen_ms, int32_t *ticks) {
     if (!h) return fail(FFMP_ERR_ARG, "handle is null");
     DeviceGuard guard(h->cfg.device);
     if (enable) {
         if (!h->tev[0][0])
             for (int i = 0; i < ffmp_handle::TIMING_RING; ++i)
-                for (int j = 0; j < 3; ++j) CK(cudaEventCreate(&h->tev[i][j]));
+                for (int j = 0; j < 4; ++j) CK(cudaEventCreate(&h->tev[i][j]));
         h->timing = true;
         h->timing_n = 0;
         return FFMP_OK;
@@ -402,16 +424,23 @@ int ffmp_timing(ffmp_handle *h, int32_t enable, float *dynamics_ms, float *obser
     double d = 0, o = 0;
     for (int i = 0; i < h->timing_n; ++i) {
         float a = 0, b = 0;
-        CK(cudaEventSynchronize(h->tev[i][2]));
+        CK(cudaEventSynchronize(h->tev[i][1]));
+        CK(cudaEventSynchronize(h->tev[i][3]));
         CK(cudaEventElapsedTime(&a, h->tev[i][0], h->tev[i][1]));
-        CK(cudaEventElapsedTime(&b, h->tev[i][1], h->tev[i][2]));
+        CK(cudaEventElapsedTime(&b, h->tev[i][2], h->tev[i][3]));
         d += a; o += b;
     }
     const int n = h->timing_n > 0 ? h->timing_n : 1;
-    if (dynamics_ms) *dynamics_ms = static_cast<float>(d / n);
-    if (observe_ms) *observe_ms = static_cast<float>(o / n);
+    if (tick_ms) *tick_ms = static_cast<float>(d / n);
+    if (regen_ms) *regen_ms = static_cast<float>(o / n);
     if (ticks) *ticks = h->timing_n;
     h->timing_n = 0;
+    return FFMP_OK;
+}
+
+int ffmp_launch_count(const ffmp_handle *h, uint64_t *out) {
+    if (!h || !out) return fail(FFMP_ERR_ARG, "null argument");
+    *out = h->launches;
     return FFMP_OK;
 }
 

@@ -106,11 +106,18 @@ class FFMPVectorEnv:
             self.scen = torch.zeros((S, N, 8), dtype=torch.int32, device=d)
             self.state = torch.zeros((N, 16), dtype=torch.int32, device=d)
             self.frames = torch.zeros((N, K, W, W), dtype=torch.uint8, device=d)
-            self.rel_goal = torch.zeros((N, 2), dtype=torch.float32, device=d)
-            self.velocity = torch.zeros((N, 2), dtype=torch.float32, device=d)
-            self.reward = torch.zeros((N,), dtype=torch.float32, device=d)
-            self.done = torch.zeros((N,), dtype=torch.uint8, device=d)
-            self.flags = torch.zeros((N,), dtype=torch.uint8, device=d)
+            # the five small per-step outputs share one block (reward | rel_goal | velocity | done | flags) so that
+            # ffmp_step_host can bring them to the host with a single copy (include/ffmp_b200.h)
+            # (N even keeps the float2 stores of the kernels 8-byte aligned; odd N falls back to separate buffers)
+            if N % 2 == 0:
+                self._out_block = torch.zeros((22 * N + 16,), dtype=torch.uint8, device=d)
+                self.reward, self.rel_goal, self.velocity, self.done, self.flags = self._split_out_block(self._out_block, N)
+            else:
+                self.reward = torch.zeros((N,), dtype=torch.float32, device=d)
+                self.rel_goal = torch.zeros((N, 2), dtype=torch.float32, device=d)
+                self.velocity = torch.zeros((N, 2), dtype=torch.float32, device=d)
+                self.done = torch.zeros((N,), dtype=torch.uint8, device=d)
+                self.flags = torch.zeros((N,), dtype=torch.uint8, device=d)
             self.term_rel_goal = torch.zeros((N, 2), dtype=torch.float32, device=d)
             self.term_velocity = torch.zeros((N, 2), dtype=torch.float32, device=d)
             self.fin_return = torch.zeros((N,), dtype=torch.float32, device=d)
@@ -128,6 +135,15 @@ class FFMPVectorEnv:
         self._is_reset = False
 
     # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _split_out_block(block, N):
+        reward = block[0:4 * N].view(torch.float32)
+        rel_goal = block[4 * N:12 * N].view(torch.float32).view(N, 2)
+        velocity = block[12 * N:20 * N].view(torch.float32).view(N, 2)
+        done = block[20 * N:21 * N]
+        flags = block[21 * N:22 * N]
+        return reward, rel_goal, velocity, done, flags
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -192,18 +208,21 @@ class FFMPVectorEnv:
         done, flags, relative_goal and velocity returned as host tensors; local_map stays on the device."""
         N = self.num_envs
         if self._host is None:
-            pin = dict(pin_memory=True)
-            self._host = {"reward": torch.empty(N, dtype=torch.float32, **pin), "done": torch.empty(N, dtype=torch.uint8, **pin),
-                          "flags": torch.empty(N, dtype=torch.uint8, **pin), "rel_goal": torch.empty((N, 2), dtype=torch.float32, **pin),
-                          "velocity": torch.empty((N, 2), dtype=torch.float32, **pin)}
+            if N % 2 == 0:
+                block = torch.zeros((22 * N + 16,), dtype=torch.uint8, pin_memory=True)
+                r, g, v, dn, fl = self._split_out_block(block, N)
+            else:
+                pin = dict(pin_memory=True)
+                r, g, v = torch.empty(N, dtype=torch.float32, **pin), torch.empty((N, 2), dtype=torch.float32, **pin), torch.empty((N, 2), dtype=torch.float32, **pin)
+                dn, fl = torch.empty(N, dtype=torch.uint8, **pin), torch.empty(N, dtype=torch.uint8, **pin)
+            self._host = {"reward": r, "rel_goal": g, "velocity": v, "done": dn, "flags": fl}
+            self._host_ptrs = tuple(C.c_void_p(self._host[k].data_ptr()) for k in ("reward", "done", "flags", "rel_goal", "velocity"))
         hst = self._host
         a = actions_host
         assert a.dtype == torch.int64 and a.device.type == "cpu" and a.numel() == N and a.is_contiguous()
         with torch.cuda.device(self.device):
-            native.check(self._L.ffmp_step_host(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(hst["reward"].data_ptr()),
-                                                C.c_void_p(hst["done"].data_ptr()), C.c_void_p(hst["flags"].data_ptr()),
-                                                C.c_void_p(hst["rel_goal"].data_ptr()), C.c_void_p(hst["velocity"].data_ptr()),
-                                                self._stream()), "ffmp_step_host")
+            native.check(self._L.ffmp_step_host(self._h, C.c_void_p(a.data_ptr()), *self._host_ptrs, self._stream()),
+                         "ffmp_step_host")
         obs = self._obs()
         obs = {"local_map": obs["local_map"], "relative_goal": hst["rel_goal"], "velocity": hst["velocity"]}
         return obs, hst["reward"], hst["done"].view(torch.bool), {"flags": hst["flags"]}
@@ -223,11 +242,17 @@ class FFMPVectorEnv:
 
     def kernel_timing(self, enable: bool):
         """enable=True: start per-kernel CUDA-event timing of the next <=256 ticks; enable=False: stop and return
-        {'dynamics_ms', 'observe_ms', 'ticks'} (averages per launch)."""
+        {'tick_ms', 'regen_ms', 'ticks'} (averages per launch: the step kernel, the background regeneration launch)."""
         d, o, n = C.c_float(), C.c_float(), C.c_int32()
         with torch.cuda.device(self.device):
             native.check(self._L.ffmp_timing(self._h, 1 if enable else 0, C.byref(d), C.byref(o), C.byref(n)), "ffmp_timing")
-        return None if enable else {"dynamics_ms": d.value, "observe_ms": o.value, "ticks": n.value}
+        return None if enable else {"tick_ms": d.value, "regen_ms": o.value, "ticks": n.value}
+
+    def launch_count(self) -> int:
+        """Kernels launched by this env since construction (step, reset and background regeneration launches)."""
+        n = C.c_uint64()
+        native.check(self._L.ffmp_launch_count(self._h, C.byref(n)), "ffmp_launch_count")
+        return n.value
 
     def error_word(self) -> int:
         w = C.c_uint32()

@@ -120,14 +120,20 @@ int ffmp_rollout(ffmp_handle *h, const int64_t *actions_dev, int32_t T, void *st
 /* Host-buffer step (the reference-facing call with HOST memory): copies actions_host (i64[N], ideally
  * pinned) to the device, steps, copies reward f32[N], done u8[N], flags u8[N], rel_goal f32[N][2] and
  * velocity f32[N][2] back (any out pointer may be NULL) and synchronises `stream`.  The local_map
- * observation stays on the device.                                                                  */
+ * observation stays on the device.  If the five bound device outputs are adjacent in memory in the order
+ * reward | rel_goal | velocity | done | flags and the five host destinations are adjacent in the same order
+ * (one 22*N-byte block each), a single device-to-host copy is issued instead of five.                */
 int ffmp_step_host(ffmp_handle *h, const int64_t *actions_host, float *reward_host, uint8_t *done_host,
                    uint8_t *flags_host, float *rel_goal_host, float *velocity_host, void *stream);
 
-/* Per-kernel device timing of the step path (CUDA events on the caller's stream around dynamics_kernel and
- * the observe kernel).  enable != 0: start recording the next (at most 256) ticks.  enable == 0: stop,
- * synchronise the recorded events and return the averages in milliseconds.                          */
-int ffmp_timing(ffmp_handle *h, int32_t enable, float *dynamics_ms, float *observe_ms, int32_t *ticks);
+/* Per-kernel device timing (CUDA events recorded by the library on the launching streams).  enable != 0: start
+ * recording the next (at most 256) ticks.  enable == 0: stop, synchronise the recorded events and return the
+ * averages in milliseconds: tick_ms = the step kernel(s) on the caller's stream, regen_ms = the background
+ * scenario-regeneration (flow-field) launch of the tick on its side stream.                             */
+int ffmp_timing(ffmp_handle *h, int32_t enable, float *tick_ms, float *regen_ms, int32_t *ticks);
+
+/* Number of kernels this handle has launched since ffmp_create (step, reset and regeneration launches). */
+int ffmp_launch_count(const ffmp_handle *h, uint64_t *out);
 
 /* Index of the newest frame slot p (1 <= p <= K-1): the observation is frames[:, p-1 : p+1]. */
 int ffmp_obs_slot(const ffmp_handle *h, int32_t *newest_slot);
