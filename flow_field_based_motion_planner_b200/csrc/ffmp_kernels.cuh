@@ -42,6 +42,7 @@ struct FlowArgs {
     uint32_t p_thresh, env_id_base;
     uint64_t seed;
     uint32_t *scen_out;
+    uint32_t neg1, one;         // 0xFFFFFFFF and 1 (set by the launcher): opaque IMAD multipliers, see flow_field.cu
 };
 
 struct StepArgs {

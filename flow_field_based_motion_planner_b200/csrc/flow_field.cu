@@ -2,21 +2,27 @@
 // Replaces the external /bev/* flow-image ROS node (/root/reference/src/train.py:84,116-121).
 //
 // Design (one WARP per grid, no block barrier anywhere):
-//   * the occupancy plane is staged into shared memory with one TMA bulk copy (cp.async.bulk +
-//     mbarrier) and packed to a bit mask: lane l owns rows [l*RPL, l*RPL+RPL) as RPL x WPR 32-bit
-//     words held in REGISTERS (G=128: 4 rows x 4 words);
-//   * the wavefront is bit-parallel: new = (west|east|north|south of frontier) & avail; left/right
-//     neighbours are funnel shifts, up/down neighbours are the adjacent row registers (one warp
-//     shuffle per boundary row); convergence is a warp vote (__any_sync);
-//   * the BFS level of a cell is recorded as Gray-code BIT-PLANES: Gray(L) differs from Gray(L-1)
-//     in bit ctz(L) only, so level L costs one XOR of `avail` into plane ctz(L) — no per-cell work
-//     inside the level loop.  Planes 0..7 live in shared memory (levels < 256), higher planes spill
-//     to a per-CTA global scratch (rare: mazes);
-//   * afterwards the planes are un-Gray'd in place; the 8-neighbour argmin is evaluated bit-parallel
-//     from cost bits 0..2 (adjacent free cells differ by exactly +-1, admissible diagonals by 0/+-2),
-//     reproducing the scan order E,NE,N,NW,W,SW,S,SE with strict '<';
-//   * cost (int32) and the flow image (u8) are expanded from the bit-planes and stored.
+//   * GEN: the scenario (SPEC.md §3) is generated from the hash RNG straight into the bit mask; otherwise the
+//     occupancy plane is staged into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier) and packed;
+//     lane l owns rows [l*RPL, l*RPL+RPL) as RPL x WPR 32-bit words held in REGISTERS (G=128: 4 rows x 4 words);
+//   * the wavefront is bit-parallel: new = (west|east|north|south of frontier) & avail; left/right neighbours are
+//     funnel shifts (SHF.L.W / SHF.R.W), up/down neighbours are the adjacent row registers (one warp shuffle per
+//     boundary row).  The loop is ALU-pipe bound (LOP3/SHF issue every other cycle per scheduler, measured in
+//     profiles/r01a_pipe_probe.txt), so everything that is not a logic op is pushed to the FMA pipe: the
+//     avail update A -= new and the boundary-lane masks are IMADs with an opaque multiplier;
+//   * the BFS level of a cell is recorded as Gray-code BIT-PLANES: Gray(L) differs from Gray(L-1) in bit ctz(L)
+//     only, so level L costs one XOR of `avail` into plane ctz(L) — no per-cell work inside the level loop.  The
+//     loop is unrolled by four levels (plane index static for three of them) and tests convergence (warp vote)
+//     once per four levels.  Planes 0/1 live in registers, 2..7 in shared memory (levels < 256), higher planes
+//     spill to a per-CTA global scratch (rare: mazes);
+//   * afterwards the planes are un-Gray'd in place; the 8-neighbour argmin is evaluated bit-parallel from cost
+//     bits 0..2 (adjacent free cells differ by exactly +-1, admissible diagonals by 0/+-2), reproducing the scan
+//     order E,NE,N,NW,W,SW,S,SE with strict '<'; direction bit-planes become flow bytes with PRMT / 8x8 bit
+//     transposes; the cost planes become bytes the same way, are staged (XOR-swizzled) in the plane storage they
+//     came from, and are widened to int32 with fully coalesced 16-byte stores.
 // Algorithmic HBM bytes: 6 B/cell (1 occ read + 4 cost write + 1 flow write).
+#include <type_traits>
+
 #include "ffmp_kernels.cuh"
 
 namespace ffmp {
@@ -50,16 +56,6 @@ struct Row {
         }
     }
 };
-
-// value of the cell at column+1 / column-1 aligned to this word
-template <int WPR>
-__device__ __forceinline__ uint32_t shr1(const uint32_t (&x)[WPR], int w) {
-    return (x[w] >> 1) | (w + 1 < WPR ? x[w + 1] << 31 : 0u);
-}
-template <int WPR>
-__device__ __forceinline__ uint32_t shl1(const uint32_t (&x)[WPR], int w) {
-    return (x[w] << 1) | (w > 0 ? x[w - 1] >> 31 : 0u);
-}
 
 // spread the 4 bits of nibble n of x to the low bit of 4 bytes
 __device__ __forceinline__ uint32_t spread4(uint32_t x, int n) {
@@ -106,14 +102,64 @@ __device__ __forceinline__ void bytes4x4(uint32_t p0, uint32_t p1, uint32_t p2, 
     out[2] = __byte_perm(b, d, 0x5410); out[3] = __byte_perm(b, d, 0x7632);
 }
 
+// funnel shifts across the words of one row: value of the cell at column-1 / column+1 aligned to word w
+template <int WPR>
+__device__ __forceinline__ uint32_t from_lo(const uint32_t (&x)[WPR], int w) {   // bit j <- cell j-1
+    return w > 0 ? __funnelshift_l(x[w - 1], x[w], 1) : x[w] << 1;
+}
+template <int WPR>
+__device__ __forceinline__ uint32_t from_hi(const uint32_t (&x)[WPR], int w) {   // bit j <- cell j+1
+    return w + 1 < WPR ? __funnelshift_r(x[w], x[w + 1], 1) : x[w] >> 1;
+}
+
+// a - n (n subset of a) and x * m (m in {0,1}) forced onto the FMA pipe (IMAD) so that they do not compete with
+// the LOP3/SHF stream on the ALU pipe: the multipliers are runtime values ptxas cannot fold into IADD/LOP3/SEL.
+__device__ __forceinline__ uint32_t sub_on_fma(uint32_t a, uint32_t n, uint32_t neg1) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(n), "r"(neg1), "r"(a));
+    return r;
+}
+__device__ __forceinline__ uint32_t mask_on_fma(uint32_t x, uint32_t m01) {
+    uint32_t r;
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(m01));
+    return r;
+}
+// replicate the sign bit of every byte over that byte (0x80.. -> 0xFF, else 0x00): PRMT with the msb of each selector nibble
+__device__ __forceinline__ uint32_t byte_sign_fill(uint32_t x) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(x));
+    return r;
+}
+
+// 32 cells x (d0..d3 direction-code planes, occupied) -> 32 flow bytes (255 occupied, else code*28), 8 words
+__device__ __forceinline__ void flow_bytes32(uint32_t d0, uint32_t d1, uint32_t d2, uint32_t d3, uint32_t occ, uint32_t (&out)[8]) {
+    uint32_t tl[4];
+    bytes4x4(d0, d1, d2, d3, tl);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        uint32_t lo = tl[b], hb = ((occ >> (8 * b)) & 0xFFu) << 24;
+        transpose8(lo, hb);          // byte j of hb:lo = code of cell 8b+j, bit 7 = occupied
+        out[2 * b] = ((lo & 0x0F0F0F0Fu) * 28u) | byte_sign_fill(lo);
+        out[2 * b + 1] = ((hb & 0x0F0F0F0Fu) * 28u) | byte_sign_fill(hb);
+    }
+}
+
+template <int K> using Int = std::integral_constant<int, K>;
+
+constexpr int NPLX = NPL + 2;   // + visited / free planes for the post-BFS phases
+constexpr int PVIS = NPL, PFREE = NPL + 1;
+
 // GEN = true : the scenario (SPEC.md §3) is generated in-kernel from the hash RNG straight into the bit
 //              mask (no occupancy plane round trip); used by the batched env (reset and regeneration).
 // GEN = false: the occupancy plane is an input (stateless operator), staged with one TMA bulk copy.
 template <int WPR, bool GEN>
 __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
     constexpr int RPL = WPR;                    // rows per lane
-    constexpr int PLANE_WORDS = 32 * RPL * WPR;  // one bit-plane of the padded (32*WPR)^2 grid
-    __shared__ __align__(128) uint32_t pl[NPL * PLANE_WORDS];
+    constexpr int P = 32 * WPR;                 // padded grid side
+    constexpr int PLANE_WORDS = 32 * RPL * WPR;  // one bit-plane of the padded grid
+    constexpr int CH = 2 * WPR;                 // 16-byte chunks per staged byte row
+    constexpr bool SWZ = (CH & (CH - 1)) == 0;
+    __shared__ __align__(128) uint32_t pl[NPLX * PLANE_WORDS];
     __shared__ __align__(8) uint64_t mbar;
 
     const int lane = threadIdx.x;
@@ -122,6 +168,8 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
     const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&mbar));
     const uint32_t pl_s = static_cast<uint32_t>(__cvta_generic_to_shared(pl));
     uint32_t *hi = a.hi_scratch + static_cast<size_t>(blockIdx.x) * (8 * PLANE_WORDS);
+    const uint32_t neg1 = a.neg1;
+    const uint32_t upm = lane == 0 ? 0u : a.one, dnm = lane == 31 ? 0u : a.one;   // boundary-lane masks (IMAD operands)
     uint32_t parity = 0;
 
     if (!GEN) {
@@ -139,7 +187,7 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
         const size_t cells = static_cast<size_t>(G) * G;
         size_t plane;
         int gi, gj;
-        uint32_t FR[RPL][WPR];
+        uint32_t A[RPL][WPR], F[RPL][WPR], G0[RPL][WPR], G1[RPL][WPR];
 
         if (GEN) {
             // ---- 1g. scenario parameters (lane 0) and the free-cell mask straight from the hash ---
@@ -155,11 +203,14 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
             sp.si = __shfl_sync(FULL, sp.si, 0); sp.sj = __shfl_sync(FULL, sp.sj, 0);
             sp.gi = __shfl_sync(FULL, sp.gi, 0); sp.gj = __shfl_sync(FULL, sp.gj, 0);
             gi = sp.gi; gj = sp.gj;
+            // rolled loop (code size): the free words go to their plane and are read back as rows below
+#pragma unroll 1
+            for (int rw = 0; rw < RPL * WPR; ++rw) {
+                const int r = rw / WPR, w = rw - r * WPR;
+                pl[pidx(PFREE, r, lane) + w] = scenario_free_word(key, lane * RPL + r, 32 * w, G, a.block_shift, a.p_thresh, sp);
+            }
 #pragma unroll
-            for (int r = 0; r < RPL; ++r)
-#pragma unroll
-                for (int w = 0; w < WPR; ++w)
-                    FR[r][w] = scenario_free_word(key, lane * RPL + r, 32 * w, G, a.block_shift, a.p_thresh, sp);
+            for (int r = 0; r < RPL; ++r) Row<WPR>::ld(&pl[pidx(PFREE, r, lane)], A[r]);
         } else {
             if (a.slot_mode) {
                 plane = static_cast<size_t>((a.episode ? a.episode[item] : a.episode_const) % a.S) * a.N + env;
@@ -204,7 +255,7 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
                     __syncwarp();
                 }
 #pragma unroll
-                for (int r = 0; r < RPL; ++r) Row<WPR>::ld(&pl[(lane * RPL + r) * WPR], FR[r]);
+                for (int r = 0; r < RPL; ++r) Row<WPR>::ld(&pl[(lane * RPL + r) * WPR], A[r]);
             } else {
                 const uint8_t *stage = reinterpret_cast<const uint8_t *>(pl);
 #pragma unroll 1
@@ -217,7 +268,7 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
                             const int col = 32 * w + lane;
                             const bool fr = (R < G && col < G) ? stage[R * G + col] == 0 : false;
                             const uint32_t bits = __ballot_sync(FULL, fr);
-                            if (lane == o) FR[r][w] = bits;
+                            if (lane == o) A[r][w] = bits;
                         }
                     }
                 }
@@ -225,110 +276,124 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
             __syncwarp();
         }
 
-        // ---- 3. zero the resident bit-planes 2.. (planes 0 and 1 live in registers during the BFS) ----
+        // ---- 3. the free mask goes to its plane; zero the resident Gray planes 2.. (0 and 1 live in registers) ----
         {
             uint32_t z[WPR];
 #pragma unroll
             for (int w = 0; w < WPR; ++w) z[w] = 0;
 #pragma unroll
-            for (int k = 2; k < NPL; ++k)
+            for (int r = 0; r < RPL; ++r) {
+                if (!GEN) Row<WPR>::st(&pl[pidx(PFREE, r, lane)], A[r]);
 #pragma unroll
-                for (int r = 0; r < RPL; ++r) Row<WPR>::st(&pl[pidx(k, r, lane)], z);
+                for (int k = 2; k < NPL; ++k) Row<WPR>::st(&pl[pidx(k, r, lane)], z);
+            }
         }
 
         // ---- 4. bit-parallel wavefront -----------------------------------------------------------
-        uint32_t A[RPL][WPR], F[RPL][WPR], G0[RPL][WPR], G1[RPL][WPR];
 #pragma unroll
         for (int r = 0; r < RPL; ++r)
 #pragma unroll
-            for (int w = 0; w < WPR; ++w) { A[r][w] = FR[r][w]; F[r][w] = 0; G0[r][w] = 0; G1[r][w] = 0; }
-        if (gi >= 0 && gj >= 0 && gi < G && gj < G && lane == gi / RPL) {
+            for (int w = 0; w < WPR; ++w) { G0[r][w] = 0; G1[r][w] = 0; }
+        {
+            // goal seeding with static register indices only (a conditional on (r, w) would turn A / F into local arrays)
+            const bool ok = gi >= 0 && gj >= 0 && gi < G && gj < G && lane == gi / RPL;
+            const int gr = gi % RPL, gw = gj >> 5;
+            const uint32_t bit = ok ? (1u << (gj & 31)) : 0u;
 #pragma unroll
             for (int r = 0; r < RPL; ++r)
 #pragma unroll
-                for (int w = 0; w < WPR; ++w)
-                    if (r == gi % RPL && w == (gj >> 5)) {
-                        const uint32_t m = (1u << (gj & 31)) & A[r][w];
-                        F[r][w] = m;
-                        A[r][w] &= ~m;
-                    }
+                for (int w = 0; w < WPR; ++w) {
+                    const uint32_t m = (r == gr && w == gw) ? (bit & A[r][w]) : 0u;
+                    F[r][w] = m;
+                    A[r][w] ^= m;
+                }
         }
-        const uint32_t upmask = lane == 0 ? 0u : 0xFFFFFFFFu, dnmask = lane == 31 ? 0u : 0xFFFFFFFFu;
-        uint32_t L = 1;
-        for (;; ++L) {
-            // Gray bit-plane update: cells with cost >= L flip Gray bit ctz(L)
-            const int k = __ffs(L) - 1;
-            if (k == 0) {
+        // one BFS level; KSEL = 0 / 1: the Gray plane of this level is G0 / G1 (registers), 2: plane ctz(L) >= 2
+        auto level = [&](auto ksel, uint32_t L) -> uint32_t {
+            constexpr int KSEL = decltype(ksel)::value;
+            if constexpr (KSEL == 0) {
 #pragma unroll
                 for (int r = 0; r < RPL; ++r)
 #pragma unroll
                     for (int w = 0; w < WPR; ++w) G0[r][w] ^= A[r][w];
-            } else if (k == 1) {
+            } else if constexpr (KSEL == 1) {
 #pragma unroll
                 for (int r = 0; r < RPL; ++r)
 #pragma unroll
                     for (int w = 0; w < WPR; ++w) G1[r][w] ^= A[r][w];
-            } else if (k < NPL) {
-#pragma unroll
-                for (int r = 0; r < RPL; ++r) {
-                    uint32_t v[WPR];
-                    uint32_t *p = &pl[pidx(k, r, lane)];
-                    Row<WPR>::ld(p, v);
-#pragma unroll
-                    for (int w = 0; w < WPR; ++w) v[w] ^= A[r][w];
-                    Row<WPR>::st(p, v);
-                }
             } else {
-                const bool first = L == (1u << k);
+                const int k = __ffs(L) - 1;
+                if (k < NPL) {
 #pragma unroll
-                for (int r = 0; r < RPL; ++r)
+                    for (int r = 0; r < RPL; ++r) {
+                        uint32_t v[WPR];
+                        uint32_t *p = &pl[pidx(k, r, lane)];
+                        Row<WPR>::ld(p, v);
 #pragma unroll
-                    for (int w = 0; w < WPR; ++w) {
-                        uint32_t *p = &hi[pidx(k - NPL, r, lane) + w];
-                        *p = first ? A[r][w] : (*p ^ A[r][w]);
+                        for (int w = 0; w < WPR; ++w) v[w] ^= A[r][w];
+                        Row<WPR>::st(p, v);
                     }
+                } else {
+                    const bool first = L == (1u << k);
+#pragma unroll
+                    for (int r = 0; r < RPL; ++r)
+#pragma unroll
+                        for (int w = 0; w < WPR; ++w) {
+                            uint32_t *p = &hi[pidx(k - NPL, r, lane) + w];
+                            *p = first ? A[r][w] : (*p ^ A[r][w]);
+                        }
+                }
             }
             uint32_t upF[WPR], dnF[WPR];
 #pragma unroll
             for (int w = 0; w < WPR; ++w) {
-                upF[w] = __shfl_up_sync(FULL, F[RPL - 1][w], 1) & upmask;
-                dnF[w] = __shfl_down_sync(FULL, F[0][w], 1) & dnmask;
+                upF[w] = mask_on_fma(__shfl_up_sync(FULL, F[RPL - 1][w], 1), upm);
+                dnF[w] = mask_on_fma(__shfl_down_sync(FULL, F[0][w], 1), dnm);
             }
             uint32_t Nw[RPL][WPR];
-            uint32_t any = 0;
 #pragma unroll
             for (int r = 0; r < RPL; ++r)
 #pragma unroll
                 for (int w = 0; w < WPR; ++w) {
                     const uint32_t up = r == 0 ? upF[w] : F[r - 1][w];
                     const uint32_t dn = r == RPL - 1 ? dnF[w] : F[r + 1][w];
-                    const uint32_t n = (shl1<WPR>(F[r], w) | shr1<WPR>(F[r], w) | up | dn) & A[r][w];
-                    Nw[r][w] = n;
-                    any |= n;
+                    Nw[r][w] = (from_lo<WPR>(F[r], w) | from_hi<WPR>(F[r], w) | up | dn) & A[r][w];
                 }
+            uint32_t any = 0;
 #pragma unroll
             for (int r = 0; r < RPL; ++r)
 #pragma unroll
-                for (int w = 0; w < WPR; ++w) { A[r][w] &= ~Nw[r][w]; F[r][w] = Nw[r][w]; }
-            if (!__any_sync(FULL, any != 0)) break;
+                for (int w = 0; w < WPR; ++w) {
+                    A[r][w] = sub_on_fma(A[r][w], Nw[r][w], neg1);
+                    F[r][w] = Nw[r][w];
+                    if constexpr (KSEL == 2) any |= Nw[r][w];
+                }
+            return any;
+        };
+        uint32_t L = 1;
+        for (;; L += 4) {
+            level(Int<0>{}, L);
+            level(Int<1>{}, L + 1);
+            level(Int<0>{}, L + 2);
+            const uint32_t any = level(Int<2>{}, L + 3);
+            if (!__any_sync(FULL, any != 0)) break;     // an empty frontier stays empty: test every fourth level
         }
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
             Row<WPR>::st(&pl[pidx(0, r, lane)], G0[r]);
             Row<WPR>::st(&pl[pidx(1, r, lane)], G1[r]);
         }
-        const uint32_t Lmax = L - 1;                       // deepest level that reached a cell
+        // level L+3 reached nothing, so the deepest level that reached a cell is <= L+2 (an over-estimate by at most
+        // three levels only makes a few zero planes take part below)
+        const uint32_t Lmax = L + 2;
         const int kmax = 32 - __clz(Lmax);                  // number of significant cost bits
-        // visited (= reached free) and free masks go to scratch planes 14/15 so that the remaining
-        // phases can be ROLLED loops over (row, word) reading memory: keeps the code inside the I-cache
-        constexpr int PVIS = 14, PFREE = 15;
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
-            uint32_t v[WPR];
+            uint32_t v[WPR], f[WPR];
+            Row<WPR>::ld(&pl[pidx(PFREE, r, lane)], f);
 #pragma unroll
-            for (int w = 0; w < WPR; ++w) v[w] = FR[r][w] & ~A[r][w];
-            Row<WPR>::st(&hi[pidx(PVIS - NPL, r, lane)], v);
-            Row<WPR>::st(&hi[pidx(PFREE - NPL, r, lane)], FR[r]);
+            for (int w = 0; w < WPR; ++w) v[w] = f[w] & ~A[r][w];
+            Row<WPR>::st(&pl[pidx(PVIS, r, lane)], v);
         }
         __syncwarp();
 
@@ -350,42 +415,143 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
         }
         __syncwarp();
 
-        // ---- 6. expand the integration field to int32 and store ---------------------------------
+        // ---- 6. flow direction, bit-parallel, and the flow image ---------------------------------
+        uint8_t *flow = a.flow + plane * cells;
+#pragma unroll 1
+        for (int r = 0; r < RPL; ++r) {
+            // rows R-1 (west, "u") and R+1 (east, "d")
+            const int lu = r == 0 ? lane - 1 : lane, ru = r == 0 ? RPL - 1 : r - 1;
+            const int ld = r == RPL - 1 ? lane + 1 : lane, rd = r == RPL - 1 ? 0 : r + 1;
+            uint32_t b0[WPR], b1c[WPR], b2c[WPR], b1u[WPR], b2u[WPR], b1d[WPR], b2d[WPR];
+            uint32_t Vc[WPR], Vu[WPR], Vd[WPR], Fc[WPR], Fu[WPR], Fd[WPR];
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) {
+                b0[w] = b1c[w] = b2c[w] = b1u[w] = b2u[w] = b1d[w] = b2d[w] = 0;
+                Vu[w] = Vd[w] = Fu[w] = Fd[w] = 0;
+            }
+            if (kmax > 0) Row<WPR>::ld(&pl[pidx(0, r, lane)], b0);
+            if (kmax > 1) Row<WPR>::ld(&pl[pidx(1, r, lane)], b1c);
+            if (kmax > 2) Row<WPR>::ld(&pl[pidx(2, r, lane)], b2c);
+            Row<WPR>::ld(&pl[pidx(PVIS, r, lane)], Vc);
+            Row<WPR>::ld(&pl[pidx(PFREE, r, lane)], Fc);
+            if (lu >= 0) {
+                if (kmax > 1) Row<WPR>::ld(&pl[pidx(1, ru, lu)], b1u);
+                if (kmax > 2) Row<WPR>::ld(&pl[pidx(2, ru, lu)], b2u);
+                Row<WPR>::ld(&pl[pidx(PVIS, ru, lu)], Vu);
+                Row<WPR>::ld(&pl[pidx(PFREE, ru, lu)], Fu);
+            }
+            if (ld < 32) {
+                if (kmax > 1) Row<WPR>::ld(&pl[pidx(1, rd, ld)], b1d);
+                if (kmax > 2) Row<WPR>::ld(&pl[pidx(2, rd, ld)], b2d);
+                Row<WPR>::ld(&pl[pidx(PVIS, rd, ld)], Vd);
+                Row<WPR>::ld(&pl[pidx(PFREE, rd, ld)], Fd);
+            }
+            const int R = lane * RPL + r;
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) {
+                const uint32_t own = Vc[w];
+                const uint32_t t = b1c[w] ^ ~b0[w];   // bit 1 of (cost-1)
+                const uint32_t u = b2c[w] ^ ~b1c[w];  // bit 2 of (cost-2)
+                // orthogonal neighbours one level lower (codes 0 E, 2 N, 4 W, 6 S)
+                const uint32_t lE = own & Vd[w] & ~(b1d[w] ^ t);
+                const uint32_t lW = own & Vu[w] & ~(b1u[w] ^ t);
+                const uint32_t lN = own & from_hi<WPR>(Vc, w) & ~(from_hi<WPR>(b1c, w) ^ t);
+                const uint32_t lS = own & from_lo<WPR>(Vc, w) & ~(from_lo<WPR>(b1c, w) ^ t);
+                // admissible diagonals two levels lower (codes 1 NE, 3 NW, 5 SW, 7 SE)
+                const uint32_t fE = Fd[w], fW = Fu[w], fN = from_hi<WPR>(Fc, w), fS = from_lo<WPR>(Fc, w);
+                const uint32_t lNE = own & from_hi<WPR>(Fd, w) & fE & fN & (from_hi<WPR>(b1d, w) ^ b1c[w]) & ~(from_hi<WPR>(b2d, w) ^ u);
+                const uint32_t lNW = own & from_hi<WPR>(Fu, w) & fW & fN & (from_hi<WPR>(b1u, w) ^ b1c[w]) & ~(from_hi<WPR>(b2u, w) ^ u);
+                const uint32_t lSW = own & from_lo<WPR>(Fu, w) & fW & fS & (from_lo<WPR>(b1u, w) ^ b1c[w]) & ~(from_lo<WPR>(b2u, w) ^ u);
+                const uint32_t lSE = own & from_lo<WPR>(Fd, w) & fE & fS & (from_lo<WPR>(b1d, w) ^ b1c[w]) & ~(from_lo<WPR>(b2d, w) ^ u);
+                const uint32_t anyD = lNE | lNW | lSW | lSE;
+                const uint32_t m0 = (anyD & lNE) | (~anyD & lE);
+                const uint32_t m1 = (anyD & lNW) | (~anyD & lN);
+                const uint32_t m2 = (anyD & lSW) | (~anyD & lW);
+                const uint32_t m3 = (anyD & lSE) | (~anyD & lS);
+                // direction code bit-planes: d0 = diagonal, (d2 d1) = quadrant, d3 = none
+                const uint32_t d1 = ~m0 & (m1 | (~m2 & m3));
+                const uint32_t d2 = ~m0 & ~m1 & (m2 | m3);
+                const uint32_t d3 = ~(m0 | m1 | m2 | m3);
+                if (R < G && 32 * w < G) {
+                    uint32_t out[8];
+                    flow_bytes32(anyD, d1, d2, d3, ~Fc[w], out);
+                    uint8_t *dst = flow + static_cast<size_t>(R) * G + 32 * w;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int col0 = 32 * w + 16 * c;
+                        if (col0 + 16 <= G && (G & 15) == 0) {   // rows are 16-byte aligned only if G % 16 == 0
+                            *reinterpret_cast<uint4 *>(dst + 16 * c) = make_uint4(out[4 * c], out[4 * c + 1], out[4 * c + 2], out[4 * c + 3]);
+                        } else {
+#pragma unroll
+                            for (int n = 0; n < 4; ++n)
+                                if (col0 + 4 * n < G) *reinterpret_cast<uint32_t *>(dst + 16 * c + 4 * n) = out[4 * c + n];
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- 7. expand the integration field to int32 and store ---------------------------------
         if (a.cost) {
             int32_t *cost = a.cost + plane * cells;
             if (kmax <= NPL) {
-                // fast path (depth < 256): 8 planes x 32 cells -> 32 bytes with 4x4 byte transposes (PRMT) and
-                // 8x8 bit-matrix transposes, then widened to int32 with INF for unreached cells
+                // fast path (depth < 256), one pass per row-of-the-lane r: the 8 plane words of the lane's row become 32
+                // cost bytes per word (PRMT byte transposes + 8x8 bit transposes); the bytes of the 32 rows of this pass
+                // are staged, XOR-swizzled, in the (k, r) slices they were read from, and every row is then widened by
+                // the whole warp with one coalesced 16-byte store per lane
+                uint8_t *stage = reinterpret_cast<uint8_t *>(pl);
 #pragma unroll 1
-                for (int rw = 0; rw < RPL * WPR; ++rw) {
-                    const int r = rw / WPR, w = rw - r * WPR;
-                    const int R = lane * RPL + r;
-                    if (R >= G || 32 * w >= G) continue;
-                    uint32_t P[NPL];
+                for (int r = 0; r < RPL; ++r) {
+                    uint32_t Bk[NPL][WPR];
 #pragma unroll
-                    for (int k = 0; k < NPL; ++k) P[k] = k < kmax ? pl[pidx(k, r, lane) + w] : 0u;
-                    const uint32_t vis = hi[pidx(PVIS - NPL, r, lane) + w];
-                    uint32_t tl[4], th[4];
-                    bytes4x4(P[0], P[1], P[2], P[3], tl);
-                    bytes4x4(P[4], P[5], P[6], P[7], th);
-                    int32_t *dst = cost + static_cast<size_t>(R) * G + 32 * w;
+                    for (int k = 0; k < NPL; ++k) Row<WPR>::ld(&pl[pidx(k, r, lane)], Bk[k]);   // planes >= kmax are zero
+                    __syncwarp();
+                    // logical staging buffer of this pass: 32 rows x P bytes, laid over the 8 slices (k', r), k' = 0..7
+                    auto phys = [&](int o) {   // byte offset in `pl` of logical byte o (o multiple of 4)
+                        constexpr int SL = 128 * WPR;          // bytes per slice
+                        return (((o / SL) * RPL + r) * 32 * WPR) * 4 + (o % SL);
+                    };
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        if (32 * w + 8 * b >= G) continue;
-                        uint32_t lo = tl[b], hb = th[b];
-                        transpose8(lo, hb);          // byte j of hb:lo = cost of cell 8b+j
-                        int4 c0, c1;
-                        c0.x = (vis >> (8 * b + 0)) & 1 ? static_cast<int>(lo & 0xFF) : COST_INF;
-                        c0.y = (vis >> (8 * b + 1)) & 1 ? static_cast<int>((lo >> 8) & 0xFF) : COST_INF;
-                        c0.z = (vis >> (8 * b + 2)) & 1 ? static_cast<int>((lo >> 16) & 0xFF) : COST_INF;
-                        c0.w = (vis >> (8 * b + 3)) & 1 ? static_cast<int>(lo >> 24) : COST_INF;
-                        c1.x = (vis >> (8 * b + 4)) & 1 ? static_cast<int>(hb & 0xFF) : COST_INF;
-                        c1.y = (vis >> (8 * b + 5)) & 1 ? static_cast<int>((hb >> 8) & 0xFF) : COST_INF;
-                        c1.z = (vis >> (8 * b + 6)) & 1 ? static_cast<int>((hb >> 16) & 0xFF) : COST_INF;
-                        c1.w = (vis >> (8 * b + 7)) & 1 ? static_cast<int>(hb >> 24) : COST_INF;
-                        *reinterpret_cast<int4 *>(dst + 8 * b) = c0;
-                        if (32 * w + 8 * b + 4 < G) *reinterpret_cast<int4 *>(dst + 8 * b + 4) = c1;
+                    for (int w = 0; w < WPR; ++w) {
+                        uint32_t tl[4], th[4];
+                        bytes4x4(Bk[0][w], Bk[1][w], Bk[2][w], Bk[3][w], tl);
+                        bytes4x4(Bk[4][w], Bk[5][w], Bk[6][w], Bk[7][w], th);
+                        uint32_t out[8];
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            uint32_t lo = tl[b], hb = th[b];
+                            transpose8(lo, hb);          // byte j of hb:lo = cost of cell 8b+j
+                            out[2 * b] = lo; out[2 * b + 1] = hb;
+                        }
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const int chunk = 2 * w + c;
+                            const int sw = SWZ ? (chunk ^ ((lane / (8 / CH)) % CH)) : chunk;
+                            *reinterpret_cast<uint4 *>(stage + phys(lane * P + 16 * sw)) =
+                                make_uint4(out[4 * c], out[4 * c + 1], out[4 * c + 2], out[4 * c + 3]);
+                        }
                     }
+                    __syncwarp();
+                    const int col = 4 * lane;
+                    if (col < G) {
+#pragma unroll 4
+                        for (int i = 0; i < 32; ++i) {
+                            const int R = i * RPL + r;
+                            if (R >= G) break;
+                            const int chunk = col >> 4;
+                            const int sw = SWZ ? (chunk ^ ((i / (8 / CH)) % CH)) : chunk;
+                            const uint32_t b4 = *reinterpret_cast<const uint32_t *>(stage + phys(i * P + 16 * sw + (col & 15)));
+                            const uint32_t vb = pl[pidx(PVIS, r, i) + (col >> 5)] >> (col & 31);
+                            int4 c;
+                            c.x = (vb & 1u) ? static_cast<int>(b4 & 0xFFu) : COST_INF;
+                            c.y = (vb & 2u) ? static_cast<int>((b4 >> 8) & 0xFFu) : COST_INF;
+                            c.z = (vb & 4u) ? static_cast<int>((b4 >> 16) & 0xFFu) : COST_INF;
+                            c.w = (vb & 8u) ? static_cast<int>(b4 >> 24) : COST_INF;
+                            *reinterpret_cast<int4 *>(cost + static_cast<size_t>(R) * G + col) = c;
+                        }
+                    }
+                    __syncwarp();
                 }
             } else {
 #pragma unroll 1
@@ -408,7 +574,7 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
 #pragma unroll
                         for (int n = 0; n < 8; ++n) hb[n] += spread4(word, n) << (k - NPL);
                     }
-                    const uint32_t vis = hi[pidx(PVIS - NPL, r, lane) + w];
+                    const uint32_t vis = pl[pidx(PVIS, r, lane) + w];
                     int32_t *dst = cost + static_cast<size_t>(R) * G + 32 * w;
 #pragma unroll
                     for (int n = 0; n < 8; ++n) {
@@ -421,104 +587,6 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
                         *reinterpret_cast<int4 *>(dst + 4 * n) = c;
                     }
                 }
-            }
-        }
-        __syncwarp();
-
-        // ---- 7. flow direction, bit-parallel -----------------------------------------------------
-        // Resident planes 3..7 are free now: 3 = visited, 4 = free (neighbour rows are read back from
-        // other lanes), 5/6/7 + plane 0 (own row only) receive the 4 direction-code bit-planes.
-        constexpr int PV = 3, PF = 4;
-#pragma unroll 1
-        for (int r = 0; r < RPL; ++r) {
-            uint32_t v[WPR];
-            Row<WPR>::ld(&hi[pidx(PVIS - NPL, r, lane)], v);
-            Row<WPR>::st(&pl[pidx(PV, r, lane)], v);
-            Row<WPR>::ld(&hi[pidx(PFREE - NPL, r, lane)], v);
-            Row<WPR>::st(&pl[pidx(PF, r, lane)], v);
-        }
-        __syncwarp();
-#pragma unroll 1
-        for (int r = 0; r < RPL; ++r) {
-            // rows R-1 (west, "u") and R+1 (east, "d")
-            const int lu = r == 0 ? lane - 1 : lane, ru = r == 0 ? RPL - 1 : r - 1;
-            const int ld = r == RPL - 1 ? lane + 1 : lane, rd = r == RPL - 1 ? 0 : r + 1;
-            uint32_t b0[WPR], b1c[WPR], b2c[WPR], b1u[WPR], b2u[WPR], b1d[WPR], b2d[WPR];
-            uint32_t Vc[WPR], Vu[WPR], Vd[WPR], Fc[WPR], Fu[WPR], Fd[WPR];
-#pragma unroll
-            for (int w = 0; w < WPR; ++w) {
-                b0[w] = b1c[w] = b2c[w] = b1u[w] = b2u[w] = b1d[w] = b2d[w] = 0;
-                Vu[w] = Vd[w] = Fu[w] = Fd[w] = 0;
-            }
-            if (kmax > 0) Row<WPR>::ld(&pl[pidx(0, r, lane)], b0);
-            if (kmax > 1) Row<WPR>::ld(&pl[pidx(1, r, lane)], b1c);
-            if (kmax > 2) Row<WPR>::ld(&pl[pidx(2, r, lane)], b2c);
-            Row<WPR>::ld(&pl[pidx(PV, r, lane)], Vc);
-            Row<WPR>::ld(&pl[pidx(PF, r, lane)], Fc);
-            if (lu >= 0) {
-                if (kmax > 1) Row<WPR>::ld(&pl[pidx(1, ru, lu)], b1u);
-                if (kmax > 2) Row<WPR>::ld(&pl[pidx(2, ru, lu)], b2u);
-                Row<WPR>::ld(&pl[pidx(PV, ru, lu)], Vu);
-                Row<WPR>::ld(&pl[pidx(PF, ru, lu)], Fu);
-            }
-            if (ld < 32) {
-                if (kmax > 1) Row<WPR>::ld(&pl[pidx(1, rd, ld)], b1d);
-                if (kmax > 2) Row<WPR>::ld(&pl[pidx(2, rd, ld)], b2d);
-                Row<WPR>::ld(&pl[pidx(PV, rd, ld)], Vd);
-                Row<WPR>::ld(&pl[pidx(PF, rd, ld)], Fd);
-            }
-            uint32_t d0[WPR], d1[WPR], d2[WPR], d3[WPR];
-#pragma unroll
-            for (int w = 0; w < WPR; ++w) {
-                const uint32_t own = Vc[w];
-                const uint32_t t = b1c[w] ^ ~b0[w];   // bit 1 of (cost-1)
-                const uint32_t u = b2c[w] ^ ~b1c[w];  // bit 2 of (cost-2)
-                // orthogonal neighbours one level lower (codes 0 E, 2 N, 4 W, 6 S)
-                const uint32_t lE = own & Vd[w] & ~(b1d[w] ^ t);
-                const uint32_t lW = own & Vu[w] & ~(b1u[w] ^ t);
-                const uint32_t lN = own & shr1<WPR>(Vc, w) & ~(shr1<WPR>(b1c, w) ^ t);
-                const uint32_t lS = own & shl1<WPR>(Vc, w) & ~(shl1<WPR>(b1c, w) ^ t);
-                // admissible diagonals two levels lower (codes 1 NE, 3 NW, 5 SW, 7 SE)
-                const uint32_t fE = Fd[w], fW = Fu[w], fN = shr1<WPR>(Fc, w), fS = shl1<WPR>(Fc, w);
-                const uint32_t lNE = own & shr1<WPR>(Fd, w) & fE & fN & (shr1<WPR>(b1d, w) ^ b1c[w]) & ~(shr1<WPR>(b2d, w) ^ u);
-                const uint32_t lNW = own & shr1<WPR>(Fu, w) & fW & fN & (shr1<WPR>(b1u, w) ^ b1c[w]) & ~(shr1<WPR>(b2u, w) ^ u);
-                const uint32_t lSW = own & shl1<WPR>(Fu, w) & fW & fS & (shl1<WPR>(b1u, w) ^ b1c[w]) & ~(shl1<WPR>(b2u, w) ^ u);
-                const uint32_t lSE = own & shl1<WPR>(Fd, w) & fE & fS & (shl1<WPR>(b1d, w) ^ b1c[w]) & ~(shl1<WPR>(b2d, w) ^ u);
-                const uint32_t anyD = lNE | lNW | lSW | lSE;
-                const uint32_t m0 = (anyD & lNE) | (~anyD & lE);
-                const uint32_t m1 = (anyD & lNW) | (~anyD & lN);
-                const uint32_t m2 = (anyD & lSW) | (~anyD & lW);
-                const uint32_t m3 = (anyD & lSE) | (~anyD & lS);
-                d0[w] = anyD;
-                d1[w] = ~m0 & (m1 | (~m2 & m3));
-                d2[w] = ~m0 & ~m1 & (m2 | m3);
-                d3[w] = ~(m0 | m1 | m2 | m3);
-            }
-            // b0 of this row is not read by any other lane: the row can be overwritten right away
-            Row<WPR>::st(&pl[pidx(0, r, lane)], d0);
-            Row<WPR>::st(&pl[pidx(5, r, lane)], d1);
-            Row<WPR>::st(&pl[pidx(6, r, lane)], d2);
-            Row<WPR>::st(&pl[pidx(7, r, lane)], d3);
-        }
-        __syncwarp();
-
-        // ---- 8. expand the flow image (255 occupied, else dir*28) and store ----------------------
-        uint8_t *flow = a.flow + plane * cells;
-#pragma unroll 1
-        for (int rw = 0; rw < RPL * WPR; ++rw) {
-            const int r = rw / WPR, w = rw - r * WPR;
-            const int R = lane * RPL + r;
-            if (R >= G || 32 * w >= G) continue;
-            const uint32_t d0 = pl[pidx(0, r, lane) + w], d1 = pl[pidx(5, r, lane) + w];
-            const uint32_t d2 = pl[pidx(6, r, lane) + w], d3 = pl[pidx(7, r, lane) + w];
-            const uint32_t occ = ~pl[pidx(PF, r, lane) + w];
-            uint8_t *dst = flow + static_cast<size_t>(R) * G + 32 * w;
-#pragma unroll
-            for (int n = 0; n < 8; ++n) {
-                if (32 * w + 4 * n >= G) continue;
-                uint32_t v = spread4(d0, n) * 28u + spread4(d1, n) * 56u + spread4(d2, n) * 112u + spread4(d3, n) * 224u;
-                v |= spread4(occ, n) * 255u;
-                *reinterpret_cast<uint32_t *>(dst + 4 * n) = v;
             }
         }
         __syncwarp();
@@ -554,16 +622,24 @@ size_t flow_field_scratch_words(int G) {
 int flow_field_max_grid(int G) {
     if (G > 128) return flow_field_large_max_grid(G);
     const int wpr = (G + 31) / 32;
-    const int smem = NPL * 32 * wpr * wpr * 4 + 1024;
+    const int smem = NPLX * 32 * wpr * wpr * 4 + 1024;
     int per_sm = (227 * 1024) / smem;
-    if (per_sm > 32) per_sm = 32;
+    if (per_sm > 16) per_sm = 16;            // ~100 registers per thread: 16 warps per SM hold the register file
     return 148 * per_sm;
 }
 
-cudaError_t launch_flow_field(const FlowArgs &a, int grid, cudaStream_t st) {
+cudaError_t launch_flow_field(const FlowArgs &a_in, int grid, cudaStream_t st) {
     if (grid <= 0) return cudaSuccess;
-    if (a.G > 128) return launch_flow_field_large(a, grid, st);
+    if (a_in.G > 128) return launch_flow_field_large(a_in, grid, st);
+    FlowArgs a = a_in;
+    a.neg1 = 0xFFFFFFFFu;
+    a.one = 1u;
     const int wpr = (a.G + 31) / 32;
+    if (!a.count_ptr && a.count > grid) {
+        // every CTA gets the same number of grids (no partial last wave)
+        const int per = (a.count + grid - 1) / grid;
+        grid = (a.count + per - 1) / per;
+    }
     if (a.generate) {
         switch (wpr) {
         case 1: flow_field_warp_kernel<1, true><<<grid, 32, 0, st>>>(a); break;
