@@ -131,6 +131,9 @@ struct ffmp_handle {
     char *list_base(int l) const { return static_cast<char *>(b.workspace) + ws.lists + ws.list_stride * l; }
     uint32_t *list_count(int l) const { return reinterpret_cast<uint32_t *>(list_base(l)); }
     uint32_t *list_ticket(int l) const { return reinterpret_cast<uint32_t *>(list_base(l)) + 1; }
+    uint32_t *list_work(int l) const { return reinterpret_cast<uint32_t *>(list_base(l)) + 2; }
+    uint32_t *reset_ticket() const { return error_word() + 4; }      // full-reset launches (same 256-byte header block)
+    uint32_t *reset_work() const { return error_word() + 5; }
     uint32_t *list_env(int l) const { return reinterpret_cast<uint32_t *>(list_base(l) + 256); }
     uint32_t *list_episode(int l) const { return list_env(l) + cfg.num_envs; }
     int64_t *actions() const { return reinterpret_cast<int64_t *>(static_cast<char *>(b.workspace) + ws.actions); }
@@ -196,7 +199,7 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
     if (tev) CK(cudaEventRecord(tev[2], h->side[l]));
     ffmp::FlowArgs fa = flow_args(h);
     fa.env_idx = h->list_env(l); fa.episode = h->list_episode(l); fa.count_ptr = h->list_count(l);
-    fa.ticket = h->list_ticket(l); fa.count_reset = h->list_count(l);
+    fa.ticket = h->list_ticket(l); fa.work = h->list_work(l); fa.count_reset = h->list_count(l);
     fa.hi_scratch = h->hi_scratch() + (static_cast<size_t>(h->ff_grid) + static_cast<size_t>(l) * h->rg_grid) * ffmp::flow_field_scratch_words(h->cfg.grid);
     CK(ffmp::launch_flow_field(fa, h->rg_grid, h->side[l]));
     if (tev) CK(cudaEventRecord(tev[3], h->side[l]));
@@ -342,6 +345,7 @@ int ffmp_reset(ffmp_handle *h, const uint8_t *mask_dev, void *stream) {
     for (int s = 0; s < c.slots; ++s) {
         ffmp::FlowArgs fa = flow_args(h);
         fa.count = c.num_envs; fa.episode_const = static_cast<uint32_t>(s);
+        if (c.grid <= 128) { fa.ticket = h->reset_ticket(); fa.work = h->reset_work(); }
         CK(ffmp::launch_flow_field(fa, h->ff_grid, st));
         h->launches += 1;
     }
@@ -485,9 +489,10 @@ int ffmp_op_scenarios(int32_t device, int32_t n, int32_t G, uint32_t p_thresh, i
 
 size_t ffmp_op_flow_field_workspace(int32_t n, int32_t G) {
     if (n <= 0 || !ffmp::flow_field_supported(G)) return 0;
-    if (G > 128) return 16;
+    if (G > 128) return 256;
     const int maxg = ffmp::flow_field_max_grid(G);
-    return static_cast<size_t>(n < maxg ? n : maxg) * ffmp::flow_field_scratch_words(G) * 4;
+    // 256-byte header (work counter, completion ticket) + the per-CTA plane scratch
+    return 256 + static_cast<size_t>(n < maxg ? n : maxg) * ffmp::flow_field_scratch_words(G) * 4;
 }
 
 int ffmp_op_flow_field(int32_t device, int32_t n, int32_t G, const uint8_t *occ_dev, const int32_t *goal_cells_dev,
@@ -503,7 +508,13 @@ int ffmp_op_flow_field(int32_t device, int32_t n, int32_t G, const uint8_t *occ_
     ffmp::FlowArgs a{};
     a.count = n; a.G = G; a.slot_mode = 0; a.S = 1; a.N = n;
     a.occ = occ_dev; a.goal_cells = goal_cells_dev; a.cost = cost_dev; a.flow = flow_dev;
-    a.hi_scratch = static_cast<uint32_t *>(workspace_dev);
+    if (reinterpret_cast<uintptr_t>(workspace_dev) % 16) return fail(FFMP_ERR_ARG, "workspace must be 16-byte aligned");
+    if (G <= 128) {
+        CK(cudaMemsetAsync(workspace_dev, 0, 16, static_cast<cudaStream_t>(stream)));
+        a.work = static_cast<uint32_t *>(workspace_dev);
+        a.ticket = a.work + 1;
+    }
+    a.hi_scratch = static_cast<uint32_t *>(workspace_dev) + 64;
     const int maxg = ffmp::flow_field_max_grid(G);
     CK(ffmp::launch_flow_field(a, n < maxg ? n : maxg, static_cast<cudaStream_t>(stream)));
     return FFMP_OK;

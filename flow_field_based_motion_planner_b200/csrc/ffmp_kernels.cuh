@@ -35,7 +35,8 @@ struct FlowArgs {
     int32_t *cost;              // may be null
     uint8_t *flow;
     uint32_t *hi_scratch;       // per-CTA spill area for cost bit-planes >= 8
-    uint32_t *ticket;           // dev u32: CTA completion ticket (slot_mode) or null
+    uint32_t *ticket;           // dev u32: CTA completion ticket or null; the last CTA re-arms ticket / work / count_reset
+    uint32_t *work;             // dev u32 (zero before the launch): dynamic grid hand-out counter, or null for striding
     uint32_t *count_reset;      // dev u32 reset to 0 by the last CTA (the regen list counter) or null
     // in-kernel scenario generation (generate = 1, slot_mode only): SPEC.md §3 parameters and the record output
     int generate, goal_mode, block_shift;

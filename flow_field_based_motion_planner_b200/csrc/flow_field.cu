@@ -29,7 +29,12 @@ namespace ffmp {
 
 namespace {
 
-constexpr int NPL = 8;  // bit-planes resident in shared memory
+constexpr int NPL = 8;   // cost bit-planes of the byte fast path (depth < 256)
+// Bit-planes 0..NPS-1 are resident in shared memory, planes NPS..15 live in the per-CTA global scratch (L2).  The operator
+// kernel needs P*P bytes of staging for the occupancy plane anyway and keeps 6 planes resident; the in-kernel-generation
+// variant runs in the background of the env step, where a small footprint matters more than its own speed, and keeps 4.
+__host__ __device__ constexpr int nps_of(bool gen) { return gen ? 4 : 6; }
+constexpr int NPG = 16 - 4;   // scratch planes per CTA (sized for the smaller resident set)
 
 template <int WPR>
 struct Row {
@@ -146,20 +151,26 @@ __device__ __forceinline__ void flow_bytes32(uint32_t d0, uint32_t d1, uint32_t 
 
 template <int K> using Int = std::integral_constant<int, K>;
 
-constexpr int NPLX = NPL + 2;   // + visited / free planes for the post-BFS phases
-constexpr int PVIS = NPL, PFREE = NPL + 1;
 
 // GEN = true : the scenario (SPEC.md §3) is generated in-kernel from the hash RNG straight into the bit
 //              mask (no occupancy plane round trip); used by the batched env (reset and regeneration).
 // GEN = false: the occupancy plane is an input (stateless operator), staged with one TMA bulk copy.
 template <int WPR, bool GEN>
-__global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
+__global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
+    constexpr int NPS = nps_of(GEN);
+    constexpr int NPLX = NPS + 2;               // + visited / free planes for the post-BFS phases
+    constexpr int PVIS = NPS, PFREE = NPS + 1;
     constexpr int RPL = WPR;                    // rows per lane
     constexpr int P = 32 * WPR;                 // padded grid side
     constexpr int PLANE_WORDS = 32 * RPL * WPR;  // one bit-plane of the padded grid
     constexpr int CH = 2 * WPR;                 // 16-byte chunks per staged byte row
     constexpr bool SWZ = (CH & (CH - 1)) == 0;
+    // cost-byte staging of one pass (32 rows x P bytes): WPR == 4 reuses dead plane storage (the free plane + the
+    // (k, r) slices of planes 0..3 just read), smaller grids have a dedicated buffer
+    constexpr bool INPLACE = WPR == 4;
+    constexpr int STAGE_WORDS = INPLACE ? 4 : 8 * P;
     __shared__ __align__(128) uint32_t pl[NPLX * PLANE_WORDS];
+    __shared__ __align__(16) uint32_t stage_buf[STAGE_WORDS];
     __shared__ __align__(8) uint64_t mbar;
 
     const int lane = threadIdx.x;
@@ -167,7 +178,7 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
     const int count = a.count_ptr ? static_cast<int>(*a.count_ptr) : a.count;
     const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&mbar));
     const uint32_t pl_s = static_cast<uint32_t>(__cvta_generic_to_shared(pl));
-    uint32_t *hi = a.hi_scratch + static_cast<size_t>(blockIdx.x) * (8 * PLANE_WORDS);
+    uint32_t *hi = a.hi_scratch + static_cast<size_t>(blockIdx.x) * (NPG * PLANE_WORDS);   // planes NPS..15
     const uint32_t neg1 = a.neg1;
     const uint32_t upm = lane == 0 ? 0u : a.one, dnm = lane == 31 ? 0u : a.one;   // boundary-lane masks (IMAD operands)
     uint32_t parity = 0;
@@ -181,8 +192,17 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
     }
 
     auto pidx = [&](int k, int r, int ln) { return ((k * RPL + r) * 32 + ln) * WPR; };
+    auto plane_ptr = [&](int k, int r, int ln) -> uint32_t * {   // resident planes in shared memory, the others in L2
+        return k < NPS ? &pl[pidx(k, r, ln)] : &hi[pidx(k - NPS, r, ln)];
+    };
 
-    for (int item = blockIdx.x; item < count; item += gridDim.x) {
+    // grids are handed out through a device counter (a.work), so warps that drew shallow grids take more of them
+    for (int item = blockIdx.x;; item += gridDim.x) {
+        if (a.work) {
+            if (lane == 0) item = static_cast<int>(atomicAdd(a.work, 1u));
+            item = __shfl_sync(FULL, item, 0);
+        }
+        if (item >= count) break;
         const uint32_t env = a.env_idx ? a.env_idx[item] : static_cast<uint32_t>(item);
         const size_t cells = static_cast<size_t>(G) * G;
         size_t plane;
@@ -221,7 +241,7 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
                 gi = a.goal_cells[2 * item];
                 gj = a.goal_cells[2 * item + 1];
             }
-            // ---- 1. TMA bulk copy of the occupancy plane into shared memory ----------------------
+            // ---- 1. TMA bulk copy of the occupancy plane into the plane storage (free before the BFS) -----------
             fence_proxy_async();  // earlier generic-proxy accesses to `pl` are ordered before the async write
             __syncwarp();
             if (lane == 0) {
@@ -231,49 +251,32 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
             mbar_wait(bar, parity);
             parity ^= 1;
 
-            // ---- 2. bytes -> free-cell bit mask (registers) --------------------------------------
-            if (G == 32 * WPR) {
-                // bit packing is linear in the flat cell index: every lane packs 16 consecutive bytes into
-                // 16 bits (conflict-free LDS.128), written in place at byte f/8; each lane then owns the
-                // WPR*WPR consecutive words of its rows
-                uint8_t *stage = reinterpret_cast<uint8_t *>(pl);
-#pragma unroll 1
-                for (int it = 0; it < (32 * WPR * WPR) / 16; ++it) {
-                    const int f = 16 * (32 * it + lane);
-                    const uint4 q = *reinterpret_cast<const uint4 *>(stage + f);
-                    const uint32_t x4[4] = {q.x, q.y, q.z, q.w};
-                    uint32_t bits = 0;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint32_t x = x4[u];
-                        const uint32_t nz = (x | ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu)) & 0x80808080u;   // 0x80 per non-zero byte
-                        const uint32_t fr = (~nz >> 7) & 0x01010101u;
-                        bits |= ((fr * 0x01020408u) >> 24 & 0xFu) << (4 * u);
-                    }
-                    __syncwarp();
-                    *reinterpret_cast<uint16_t *>(stage + (f >> 3)) = static_cast<uint16_t>(bits);
-                    __syncwarp();
-                }
-#pragma unroll
-                for (int r = 0; r < RPL; ++r) Row<WPR>::ld(&pl[(lane * RPL + r) * WPR], A[r]);
-            } else {
+            // ---- 2. bytes -> free-cell bit mask: one byte per lane and one warp vote per 32 cells; the vote lands in
+            //      the register of the lane that owns the row (static register indices, rolled over the owner lane) ----
+            {
                 const uint8_t *stage = reinterpret_cast<const uint8_t *>(pl);
 #pragma unroll 1
                 for (int o = 0; o < 32; ++o) {
+                    const bool mine = lane == o;
 #pragma unroll
                     for (int r = 0; r < RPL; ++r) {
                         const int R = o * RPL + r;
 #pragma unroll
                         for (int w = 0; w < WPR; ++w) {
-                            const int col = 32 * w + lane;
-                            const bool fr = (R < G && col < G) ? stage[R * G + col] == 0 : false;
+                            bool fr;
+                            if (G == 32 * WPR) {
+                                fr = stage[(R * WPR + w) * 32 + lane] == 0;
+                            } else {
+                                const int col = 32 * w + lane;
+                                fr = (R < G && col < G) ? stage[R * G + col] == 0 : false;
+                            }
                             const uint32_t bits = __ballot_sync(FULL, fr);
-                            if (lane == o) A[r][w] = bits;
+                            if (mine) A[r][w] = bits;
                         }
                     }
                 }
+                __syncwarp();
             }
-            __syncwarp();
         }
 
         // ---- 3. the free mask goes to its plane; zero the resident Gray planes 2.. (0 and 1 live in registers) ----
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
             for (int r = 0; r < RPL; ++r) {
                 if (!GEN) Row<WPR>::st(&pl[pidx(PFREE, r, lane)], A[r]);
 #pragma unroll
-                for (int k = 2; k < NPL; ++k) Row<WPR>::st(&pl[pidx(k, r, lane)], z);
+                for (int k = 2; k < NPS; ++k) Row<WPR>::st(&pl[pidx(k, r, lane)], z);
             }
         }
 
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
                     for (int w = 0; w < WPR; ++w) G1[r][w] ^= A[r][w];
             } else {
                 const int k = __ffs(L) - 1;
-                if (k < NPL) {
+                if (k < NPS) {
 #pragma unroll
                     for (int r = 0; r < RPL; ++r) {
                         uint32_t v[WPR];
@@ -339,7 +342,7 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
                     for (int r = 0; r < RPL; ++r)
 #pragma unroll
                         for (int w = 0; w < WPR; ++w) {
-                            uint32_t *p = &hi[pidx(k - NPL, r, lane) + w];
+                            uint32_t *p = &hi[pidx(k - NPS, r, lane) + w];
                             *p = first ? A[r][w] : (*p ^ A[r][w]);
                         }
                 }
@@ -397,16 +400,48 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
         }
         __syncwarp();
 
-        // ---- 5. Gray -> binary, in place ---------------------------------------------------------
+        // ---- 5. Gray -> binary, in place.  The (rarely more than two) planes that live in the global scratch are
+        //      loaded up front as independent requests, so their L2 latency is paid once per row, not once per plane ----
 #pragma unroll 1
         for (int r = 0; r < RPL; ++r) {
             uint32_t acc[WPR];
 #pragma unroll
             for (int w = 0; w < WPR; ++w) acc[w] = 0;
+            int k = kmax - 1;
 #pragma unroll 1
-            for (int k = kmax - 1; k >= 0; --k) {
+            for (; k >= NPS + 4; --k) {          // deep maps only (depth >= 1024)
                 uint32_t v[WPR];
-                uint32_t *p = k < NPL ? &pl[pidx(k, r, lane)] : &hi[pidx(k - NPL, r, lane)];
+                uint32_t *p = plane_ptr(k, r, lane);
+                Row<WPR>::ld(p, v);
+#pragma unroll
+                for (int w = 0; w < WPR; ++w) { acc[w] ^= v[w]; v[w] = acc[w]; }
+                Row<WPR>::st(p, v);
+            }
+            if (k >= NPS) {
+                uint32_t g[4][WPR];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (NPS + j <= k) {
+                        Row<WPR>::ld(plane_ptr(NPS + j, r, lane), g[j]);
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < WPR; ++w) g[j][w] = 0;
+                    }
+                }
+#pragma unroll
+                for (int j = 3; j >= 0; --j) {
+                    if (NPS + j <= k) {
+#pragma unroll
+                        for (int w = 0; w < WPR; ++w) { acc[w] ^= g[j][w]; g[j][w] = acc[w]; }
+                        Row<WPR>::st(plane_ptr(NPS + j, r, lane), g[j]);
+                    }
+                }
+                k = NPS - 1;
+            }
+#pragma unroll 1
+            for (; k >= 0; --k) {
+                uint32_t v[WPR];
+                uint32_t *p = &pl[pidx(k, r, lane)];
                 Row<WPR>::ld(p, v);
 #pragma unroll
                 for (int w = 0; w < WPR; ++w) { acc[w] ^= v[w]; v[w] = acc[w]; }
@@ -500,17 +535,30 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
                 // cost bytes per word (PRMT byte transposes + 8x8 bit transposes); the bytes of the 32 rows of this pass
                 // are staged, XOR-swizzled, in the (k, r) slices they were read from, and every row is then widened by
                 // the whole warp with one coalesced 16-byte store per lane
-                uint8_t *stage = reinterpret_cast<uint8_t *>(pl);
+                uint8_t *pl8 = reinterpret_cast<uint8_t *>(pl);
 #pragma unroll 1
                 for (int r = 0; r < RPL; ++r) {
                     uint32_t Bk[NPL][WPR];
 #pragma unroll
-                    for (int k = 0; k < NPL; ++k) Row<WPR>::ld(&pl[pidx(k, r, lane)], Bk[k]);   // planes >= kmax are zero
+                    for (int k = 0; k < NPL; ++k) {
+                        if (k < kmax) {
+                            Row<WPR>::ld(plane_ptr(k, r, lane), Bk[k]);
+                        } else {
+#pragma unroll
+                            for (int w = 0; w < WPR; ++w) Bk[k][w] = 0;
+                        }
+                    }
                     __syncwarp();
-                    // logical staging buffer of this pass: 32 rows x P bytes, laid over the 8 slices (k', r), k' = 0..7
-                    auto phys = [&](int o) {   // byte offset in `pl` of logical byte o (o multiple of 4)
-                        constexpr int SL = 128 * WPR;          // bytes per slice
-                        return (((o / SL) * RPL + r) * 32 * WPR) * 4 + (o % SL);
+                    // logical staging buffer of this pass: 32 rows x P bytes
+                    auto phys = [&](int o) -> uint8_t * {   // address of logical byte o (o multiple of 4)
+                        if constexpr (INPLACE) {
+                            constexpr int PB = PLANE_WORDS * 4, SL = 128 * WPR;    // bytes per plane / per (k, r) slice
+                            if (o < PB) return pl8 + PFREE * PB + o;               // the free plane is dead by now
+                            const int q = o - PB;
+                            return pl8 + (((q / SL) * RPL + r) * 32 * WPR) * 4 + (q % SL);   // slice (k = q / SL, r) of planes 0..3
+                        } else {
+                            return reinterpret_cast<uint8_t *>(stage_buf) + o;
+                        }
                     };
 #pragma unroll
                     for (int w = 0; w < WPR; ++w) {
@@ -528,7 +576,7 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
                         for (int c = 0; c < 2; ++c) {
                             const int chunk = 2 * w + c;
                             const int sw = SWZ ? (chunk ^ ((lane / (8 / CH)) % CH)) : chunk;
-                            *reinterpret_cast<uint4 *>(stage + phys(lane * P + 16 * sw)) =
+                            *reinterpret_cast<uint4 *>(phys(lane * P + 16 * sw)) =
                                 make_uint4(out[4 * c], out[4 * c + 1], out[4 * c + 2], out[4 * c + 3]);
                         }
                     }
@@ -541,7 +589,7 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
                             if (R >= G) break;
                             const int chunk = col >> 4;
                             const int sw = SWZ ? (chunk ^ ((i / (8 / CH)) % CH)) : chunk;
-                            const uint32_t b4 = *reinterpret_cast<const uint32_t *>(stage + phys(i * P + 16 * sw + (col & 15)));
+                            const uint32_t b4 = *reinterpret_cast<const uint32_t *>(phys(i * P + 16 * sw + (col & 15)));
                             const uint32_t vb = pl[pidx(PVIS, r, i) + (col >> 5)] >> (col & 31);
                             int4 c;
                             c.x = (vb & 1u) ? static_cast<int>(b4 & 0xFFu) : COST_INF;
@@ -564,13 +612,13 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
                     for (int n = 0; n < 8; ++n) { lo[n] = 0; hb[n] = 0; }
 #pragma unroll 1
                     for (int k = 0; k < NPL; ++k) {
-                        const uint32_t word = pl[pidx(k, r, lane) + w];
+                        const uint32_t word = plane_ptr(k, r, lane)[w];
 #pragma unroll
                         for (int n = 0; n < 8; ++n) lo[n] += spread4(word, n) << k;
                     }
 #pragma unroll 1
                     for (int k = NPL; k < kmax; ++k) {
-                        const uint32_t word = hi[pidx(k - NPL, r, lane) + w];
+                        const uint32_t word = plane_ptr(k, r, lane)[w];
 #pragma unroll
                         for (int n = 0; n < 8; ++n) hb[n] += spread4(word, n) << (k - NPL);
                     }
@@ -598,6 +646,7 @@ __global__ void __launch_bounds__(32) flow_field_warp_kernel(FlowArgs a) {
         const uint32_t t = atomicAdd(a.ticket, 1u);
         if (t == gridDim.x - 1) {
             *a.ticket = 0;
+            if (a.work) *a.work = 0;
             if (a.count_reset) *a.count_reset = 0;
             __threadfence();
         }
@@ -614,17 +663,17 @@ bool flow_field_supported(int G) { return (G >= 16 && G <= 128 && (G % 4) == 0) 
 
 size_t flow_field_scratch_words(int G) {
     if (G > 128) return 0;   // the large-map kernel keeps everything in shared memory and the cost plane
-    // spill planes for cost bits 8..15 of the padded grid ((G+31)/32*32)^2
+    // planes NPS..15 of the padded grid ((G+31)/32*32)^2 live in the per-CTA scratch (L2 resident)
     const int wpr = (G + 31) / 32;
-    return static_cast<size_t>(8) * 32 * wpr * wpr;
+    return static_cast<size_t>(NPG) * 32 * wpr * wpr;
 }
 
 int flow_field_max_grid(int G) {
     if (G > 128) return flow_field_large_max_grid(G);
     const int wpr = (G + 31) / 32;
-    const int smem = NPLX * 32 * wpr * wpr * 4 + 1024;
+    const int smem = (nps_of(false) + 2) * 32 * wpr * wpr * 4 + (wpr == 4 ? 16 : 32 * 32 * wpr) + 1024 + 16;
     int per_sm = (227 * 1024) / smem;
-    if (per_sm > 16) per_sm = 16;            // ~100 registers per thread: 16 warps per SM hold the register file
+    if (per_sm > 16) per_sm = 16;            // __launch_bounds__(32, 16): 128 registers per thread
     return 148 * per_sm;
 }
 
@@ -635,11 +684,7 @@ cudaError_t launch_flow_field(const FlowArgs &a_in, int grid, cudaStream_t st) {
     a.neg1 = 0xFFFFFFFFu;
     a.one = 1u;
     const int wpr = (a.G + 31) / 32;
-    if (!a.count_ptr && a.count > grid) {
-        // every CTA gets the same number of grids (no partial last wave)
-        const int per = (a.count + grid - 1) / grid;
-        grid = (a.count + per - 1) / per;
-    }
+    if (a.work && !a.ticket) return cudaErrorInvalidValue;   // the work counter is re-armed by the ticket holder
     if (a.generate) {
         switch (wpr) {
         case 1: flow_field_warp_kernel<1, true><<<grid, 32, 0, st>>>(a); break;

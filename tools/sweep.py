@@ -10,6 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import flow_field_based_motion_planner_b200 as ffmp  # noqa: E402
 
 dev = torch.device("cuda:0")
+torch.manual_seed(1234)
 
 
 def run_env(tag, steps=2000, **kw):
