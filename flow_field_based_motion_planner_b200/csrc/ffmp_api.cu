@@ -126,6 +126,7 @@ struct ffmp_handle {
     int timing_n = 0;
     cudaEvent_t tev[TIMING_RING][4];
     uint64_t launches = 0;          // kernels launched by this handle (ffmp_launch_count)
+    unsigned long long *trace = nullptr;   // FFMP_TRACE=1: [N][8] tick-kernel timestamps (library-owned, diagnostics only)
 
     uint32_t *error_word() const { return reinterpret_cast<uint32_t *>(static_cast<char *>(b.workspace) + ws.error_word); }
     char *list_base(int l) const { return static_cast<char *>(b.workspace) + ws.lists + ws.list_stride * l; }
@@ -166,6 +167,7 @@ ffmp::StepArgs step_args(const ffmp_handle *h) {
     a.done = b.done; a.flags = b.flags; a.fin_length = b.fin_length;
     a.error_word = h->error_word();
     a.obs_order = h->obs_order();
+    a.trace = h->trace;
     return a;
 }
 
@@ -258,6 +260,12 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
         ffmp_destroy(h);
         return fail(FFMP_ERR_CUDA, "stream/event creation", ce);
     }
+    if (const char *t = std::getenv("FFMP_TRACE")) {
+        if (std::atoi(t) != 0 && cudaMalloc(&h->trace, static_cast<size_t>(cfg->num_envs) * 8 * sizeof(unsigned long long)) != cudaSuccess) {
+            cudaGetLastError();
+            h->trace = nullptr;
+        }
+    }
     const int maxg = ffmp::flow_field_max_grid(cfg->grid);
     h->ff_grid = cfg->num_envs < maxg ? cfg->num_envs : maxg;
     h->rg_grid = cfg->num_envs < REGEN_GRID ? cfg->num_envs : REGEN_GRID;
@@ -320,6 +328,7 @@ int ffmp_destroy(ffmp_handle *h) {
         if (h->ev_step[i]) cudaEventDestroy(h->ev_step[i]);
         if (h->ev_regen[i]) cudaEventDestroy(h->ev_regen[i]);
     }
+    if (h->trace) cudaFree(h->trace);
     if (h->tev[0][0])
         for (int i = 0; i < ffmp_handle::TIMING_RING; ++i)
             for (int j = 0; j < 4; ++j) cudaEventDestroy(h->tev[i][j]);
@@ -439,6 +448,16 @@ int ffmp_timing(ffmp_handle *h, int32_t enable, float *tick_ms, float *regen_ms,
     if (regen_ms) *regen_ms = static_cast<float>(o / n);
     if (ticks) *ticks = h->timing_n;
     h->timing_n = 0;
+    return FFMP_OK;
+}
+
+int ffmp_debug_trace(ffmp_handle *h, uint64_t *out_host, void *stream) {
+    if (!h || !out_host) return fail(FFMP_ERR_ARG, "null argument");
+    if (!h->trace) return fail(FFMP_ERR_STATE, "tracing is off (set FFMP_TRACE=1 before ffmp_create)");
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaMemcpyAsync(out_host, h->trace, static_cast<size_t>(h->cfg.num_envs) * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return FFMP_OK;
 }
 

@@ -64,6 +64,7 @@ struct StepArgs {
     uint32_t *regen_env, *regen_episode, *regen_count;  // regeneration request list
     uint32_t *obs_order;        // [N][8] crop orders, dynamics_kernel -> observe_kernel
     uint32_t *error_word;
+    unsigned long long *trace;  // optional [N][8] per-CTA timestamps of the tick kernel (diagnostics, FFMP_TRACE=1) or null
 };
 
 struct RewarderArgs {

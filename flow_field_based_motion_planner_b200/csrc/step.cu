@@ -465,6 +465,20 @@ __global__ void __launch_bounds__(128) tick_tma_kernel(const __grid_constant__ C
     const uint32_t tile_s = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
     const uint32_t bytes = static_cast<uint32_t>(tile_w * W);
     const int half = W >> 1;
+    unsigned long long *tr = a.trace ? a.trace + static_cast<size_t>(e) * 8 : nullptr;
+    auto stamp = [&](int slot) {
+        if (tr && tid == 0) {
+            if (slot == 0 || slot == 7) {
+                unsigned long long g;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+                tr[slot] = g;
+            } else {
+                tr[slot] = static_cast<unsigned long long>(clock64());
+            }
+        }
+    };
+    stamp(0);
+    stamp(1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -500,6 +514,7 @@ __global__ void __launch_bounds__(128) tick_tma_kernel(const __grid_constant__ C
             ci = robot_cell(nx);
             cj = robot_cell(ny);
             const int i0 = ci - half, j0 = cj - half;
+            stamp(2);
             if (lane == 0) {   // speculative window fetch: the episode usually continues
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
                 tma_window(tile_s, &tmap, j0 & ~15, i0, static_cast<int>((episode % a.S) * a.N + e), bar);
@@ -511,7 +526,9 @@ __global__ void __launch_bounds__(128) tick_tma_kernel(const __grid_constant__ C
             const float vl = dist_spec(fsub(nx, x), fsub(ny, y));
             const float va = pi_to_pi(fsub(nyaw, yaw));
             const bool goal = d < 0.5f;
+            stamp(3);
             mbar_wait_parity(bar, 0);
+            stamp(4);
             bool hit = false;
             if (lane < 21) {
                 const int di = FOOT_DI[lane], dj = FOOT_DJ[lane];
@@ -603,6 +620,7 @@ __global__ void __launch_bounds__(128) tick_tma_kernel(const __grid_constant__ C
     const int i0 = ci - half, j0 = cj - half;
     uint32_t parity = static_cast<uint32_t>(sh.parity);
     mbar_wait_parity(bar, parity);
+    stamp(5);
 
     uint32_t *f_new = reinterpret_cast<uint32_t *>(a.frames + (static_cast<size_t>(e) * a.K + a.slot_new) * W * W);
     uint32_t *f_old = f_new - (W * W >> 2);
@@ -646,6 +664,14 @@ __global__ void __launch_bounds__(128) tick_tma_kernel(const __grid_constant__ C
             for (int w2 = lane; w2 < wpr; w2 += 32)
                 drain_tile<false>(tile32, tile_wpr, G, W, wpr, p0, q0 & 15, warp, 4, w2, colmask(q0, w2), f_old, nullptr);
         }
+    }
+    __syncthreads();
+    stamp(6);
+    stamp(7);
+    if (tr && tid == 0) {
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        tr[1] = (tr[1] << 8) | smid;     // clock at start (shifted) + SM id in the low byte
     }
 }
 

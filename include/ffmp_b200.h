@@ -135,6 +135,11 @@ int ffmp_timing(ffmp_handle *h, int32_t enable, float *tick_ms, float *regen_ms,
 /* Number of kernels this handle has launched since ffmp_create (step, reset and regeneration launches). */
 int ffmp_launch_count(const ffmp_handle *h, uint64_t *out);
 
+/* Diagnostics: with FFMP_TRACE=1 in the environment at ffmp_create, the tick kernel records eight timestamps per env
+ * (u64[N][8]: globaltimer at start, clock<<8|smid, clock after kinematics, before / after the window wait, at the
+ * start of the drain, at the end, globaltimer at the end) of its latest launch.  Copies them out; synchronises `stream`. */
+int ffmp_debug_trace(ffmp_handle *h, uint64_t *out_host, void *stream);
+
 /* Index of the newest frame slot p (1 <= p <= K-1): the observation is frames[:, p-1 : p+1]. */
 int ffmp_obs_slot(const ffmp_handle *h, int32_t *newest_slot);
 
