@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libffmp_b200.so")
+LIB_PATH = os.environ.get("FFMP_LIB_PATH") or os.path.join(HERE, "csrc", "libffmp_b200.so")   # override: A/B builds while tuning
 ABI_VERSION = 1
 COST_INF = 0x7FFFFFFF
 
