@@ -510,7 +510,6 @@ int ffmp_op_scenarios(int32_t device, int32_t n, int32_t G, uint32_t p_thresh, i
 
 size_t ffmp_op_flow_field_workspace(int32_t n, int32_t G) {
     if (n <= 0 || !ffmp::flow_field_supported(G)) return 0;
-    if (G > 128) return 256;
     const int maxg = ffmp::flow_field_max_grid(G);
     // 256-byte header (work counter, completion ticket) + the per-CTA plane scratch
     return 256 + static_cast<size_t>(n < maxg ? n : maxg) * ffmp::flow_field_scratch_words(G) * 4;

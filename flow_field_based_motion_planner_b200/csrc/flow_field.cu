@@ -23,7 +23,7 @@
 // Algorithmic HBM bytes: 6 B/cell (1 occ read + 4 cost write + 1 flow write).
 #include <type_traits>
 
-#include "ffmp_kernels.cuh"
+#include "flow_bits.cuh"
 
 namespace ffmp {
 
@@ -35,119 +35,6 @@ constexpr int NPL = 8;   // cost bit-planes of the byte fast path (depth < 256)
 // variant runs in the background of the env step, where a small footprint matters more than its own speed, and keeps 4.
 __host__ __device__ constexpr int nps_of(bool gen) { return gen ? 4 : 6; }
 constexpr int NPG = 16 - 4;   // scratch planes per CTA (sized for the smaller resident set)
-
-template <int WPR>
-struct Row {
-    static __device__ __forceinline__ void ld(const uint32_t *p, uint32_t (&v)[WPR]) {
-        if constexpr (WPR == 4) {
-            const uint4 t = *reinterpret_cast<const uint4 *>(p);
-            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-        } else if constexpr (WPR == 2) {
-            const uint2 t = *reinterpret_cast<const uint2 *>(p);
-            v[0] = t.x; v[1] = t.y;
-        } else {
-#pragma unroll
-            for (int w = 0; w < WPR; ++w) v[w] = p[w];
-        }
-    }
-    static __device__ __forceinline__ void st(uint32_t *p, const uint32_t (&v)[WPR]) {
-        if constexpr (WPR == 4) {
-            *reinterpret_cast<uint4 *>(p) = make_uint4(v[0], v[1], v[2], v[3]);
-        } else if constexpr (WPR == 2) {
-            *reinterpret_cast<uint2 *>(p) = make_uint2(v[0], v[1]);
-        } else {
-#pragma unroll
-            for (int w = 0; w < WPR; ++w) p[w] = v[w];
-        }
-    }
-};
-
-// spread the 4 bits of nibble n of x to the low bit of 4 bytes
-__device__ __forceinline__ uint32_t spread4(uint32_t x, int n) {
-    return (((x >> (4 * n)) & 0xFu) * 0x00204081u) & 0x01010101u;
-}
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// 8x8 bit-matrix transpose of the 64-bit value hi:lo (Hacker's Delight 7-3), on 32-bit halves
-__device__ __forceinline__ void transpose8(uint32_t &lo, uint32_t &hi) {
-    uint32_t t;
-    t = (lo ^ (lo >> 7)) & 0x00AA00AAu; lo ^= t ^ (t << 7);
-    t = (hi ^ (hi >> 7)) & 0x00AA00AAu; hi ^= t ^ (t << 7);
-    t = (lo ^ (lo >> 14)) & 0x0000CCCCu; lo ^= t ^ (t << 14);
-    t = (hi ^ (hi >> 14)) & 0x0000CCCCu; hi ^= t ^ (t << 14);
-    t = (lo ^ __funnelshift_r(lo, hi, 28)) & 0xF0F0F0F0u;
-    lo ^= t; hi ^= t >> 4;
-}
-
-// 4x4 byte transpose: out[b] = (p0.b, p1.b, p2.b, p3.b)
-__device__ __forceinline__ void bytes4x4(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t (&out)[4]) {
-    const uint32_t a = __byte_perm(p0, p1, 0x5140), b = __byte_perm(p0, p1, 0x7362);
-    const uint32_t c = __byte_perm(p2, p3, 0x5140), d = __byte_perm(p2, p3, 0x7362);
-    out[0] = __byte_perm(a, c, 0x5410); out[1] = __byte_perm(a, c, 0x7632);
-    out[2] = __byte_perm(b, d, 0x5410); out[3] = __byte_perm(b, d, 0x7632);
-}
-
-// funnel shifts across the words of one row: value of the cell at column-1 / column+1 aligned to word w
-template <int WPR>
-__device__ __forceinline__ uint32_t from_lo(const uint32_t (&x)[WPR], int w) {   // bit j <- cell j-1
-    return w > 0 ? __funnelshift_l(x[w - 1], x[w], 1) : x[w] << 1;
-}
-template <int WPR>
-__device__ __forceinline__ uint32_t from_hi(const uint32_t (&x)[WPR], int w) {   // bit j <- cell j+1
-    return w + 1 < WPR ? __funnelshift_r(x[w], x[w + 1], 1) : x[w] >> 1;
-}
-
-// a - n (n subset of a) and x * m (m in {0,1}) forced onto the FMA pipe (IMAD) so that they do not compete with
-// the LOP3/SHF stream on the ALU pipe: the multipliers are runtime values ptxas cannot fold into IADD/LOP3/SEL.
-__device__ __forceinline__ uint32_t sub_on_fma(uint32_t a, uint32_t n, uint32_t neg1) {
-    uint32_t r;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(n), "r"(neg1), "r"(a));
-    return r;
-}
-__device__ __forceinline__ uint32_t mask_on_fma(uint32_t x, uint32_t m01) {
-    uint32_t r;
-    asm("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(m01));
-    return r;
-}
-// replicate the sign bit of every byte over that byte (0x80.. -> 0xFF, else 0x00): PRMT with the msb of each selector nibble
-__device__ __forceinline__ uint32_t byte_sign_fill(uint32_t x) {
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(x));
-    return r;
-}
-
-// 32 cells x (d0..d3 direction-code planes, occupied) -> 32 flow bytes (255 occupied, else code*28), 8 words
-__device__ __forceinline__ void flow_bytes32(uint32_t d0, uint32_t d1, uint32_t d2, uint32_t d3, uint32_t occ, uint32_t (&out)[8]) {
-    uint32_t tl[4];
-    bytes4x4(d0, d1, d2, d3, tl);
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        uint32_t lo = tl[b], hb = ((occ >> (8 * b)) & 0xFFu) << 24;
-        transpose8(lo, hb);          // byte j of hb:lo = code of cell 8b+j, bit 7 = occupied
-        out[2 * b] = ((lo & 0x0F0F0F0Fu) * 28u) | byte_sign_fill(lo);
-        out[2 * b + 1] = ((hb & 0x0F0F0F0Fu) * 28u) | byte_sign_fill(hb);
-    }
-}
 
 template <int K> using Int = std::integral_constant<int, K>;
 
@@ -657,12 +544,13 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
 
 bool flow_field_large_supported(int G);
 int flow_field_large_max_grid(int G);
+size_t flow_field_large_scratch_words(int G);
 cudaError_t launch_flow_field_large(const FlowArgs &a, int grid, cudaStream_t st);
 
 bool flow_field_supported(int G) { return (G >= 16 && G <= 128 && (G % 4) == 0) || flow_field_large_supported(G); }
 
 size_t flow_field_scratch_words(int G) {
-    if (G > 128) return 0;   // the large-map kernel keeps everything in shared memory and the cost plane
+    if (G > 128) return flow_field_large_scratch_words(G);
     // planes NPS..15 of the padded grid ((G+31)/32*32)^2 live in the per-CTA scratch (L2 resident)
     const int wpr = (G + 31) / 32;
     return static_cast<size_t>(NPG) * 32 * wpr * wpr;

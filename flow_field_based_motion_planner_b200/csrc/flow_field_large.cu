@@ -1,157 +1,342 @@
-// flow_field_large.cu — SPEC.md §4/§5 for large maps (128 < G <= 512, G % 32 == 0): one CTA per grid.
+// flow_field_large.cu — SPEC.md §4/§5 for large maps (128 < G <= 512, G % 32 == 0): one CTA per grid, one THREAD per row.
 //
-// The 128x128 path keeps a whole grid in the registers of one warp; a 512x512 grid (BASELINE config 4) is
-// 32 KB per bit mask, so here the masks live in shared memory (avail, two frontier buffers, free:
-// 4 x G^2/8 bytes = 128 KB at G=512) and 1024 threads sweep the words of the bit-parallel wavefront with
-// one __syncthreads_or per level.  Words whose 3x3 word neighbourhood holds no frontier bit are skipped
-// after one shared-memory probe.  The level of a cell is stored to the int32 cost plane when its bit
-// first sets; the direction pass then reads the (L2-resident) cost plane.  First correct version: the
-// per-level barrier makes it latency-bound; a cluster / DSMEM variant is the planned follow-up.
-#include "ffmp_kernels.cuh"
+// The 128x128 kernel keeps a whole grid in the registers of one warp.  A 512x512 grid is 32 KB per bit mask, so here a
+// CTA of P threads (P = 256 or 512 padded rows) owns the grid: thread t holds row t of the avail / frontier masks as WPR
+// 32-bit words in REGISTERS (16 words at G = 512), exactly the per-lane layout of the small kernel with one row per lane,
+// and the same ALU-lean wavefront step (funnel shifts + two LOP3 per word, avail update on the FMA pipe).  Rows above /
+// below are warp shuffles; the rows at warp boundaries are exchanged through a double-buffered shared-memory array, and
+// one __syncthreads_or per level both publishes them and tests convergence.  BFS levels are recorded as Gray-code
+// bit-planes: plane 0 in registers, planes 1..NPSL in shared memory, the rest (touched every 2^(k+1) levels) in a per-CTA
+// global scratch that stays in L2.  Afterwards each thread un-Grays its row, evaluates the 8-neighbour argmin bit-parallel
+// (neighbour rows from the shared-memory planes), and writes its row of the flow image and of the int32 integration field:
+// one word of the mask is exactly one 128-byte line of cost, so the per-thread 16-byte stores fill whole lines.
+// Algorithmic HBM bytes: 6 B/cell (1 occ read + 4 cost write + 1 flow write).
+#include "flow_bits.cuh"
 
 namespace ffmp {
 
 namespace {
 
-constexpr int LARGE_THREADS = 1024;
+constexpr int NPSL = 3;               // shared-memory Gray planes 1..NPSL (plane 0 lives in registers)
+constexpr int NPMAX = 18;             // cost bits: depth < 2^18 = 512 * 512
+constexpr int NPGL = NPMAX - 1 - NPSL;   // planes NPSL+1..17 in the global scratch
+constexpr int NSM = NPSL + 2;         // shared-memory planes per CTA: 1..NPSL, visited, free
 
-struct LargeShared {
+struct LargeInfo {
     unsigned long long plane;
     int gi, gj;
     uint32_t key;
     ScenarioParams sp;
 };
 
-template <bool GEN>
-__global__ void __launch_bounds__(LARGE_THREADS) flow_field_cta_kernel(FlowArgs a) {
-    extern __shared__ __align__(16) uint32_t sm[];
-    __shared__ LargeShared sh;
+// 16 occupancy bytes -> 16 free bits (bit = 1: byte == 0)
+__device__ __forceinline__ uint32_t pack16(const uint4 q) {
+    const uint32_t x4[4] = {q.x, q.y, q.z, q.w};
+    uint32_t bits = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const uint32_t x = x4[u];
+        const uint32_t nz = (x | ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu)) & 0x80808080u;   // 0x80 per non-zero byte
+        const uint32_t fr = (~nz >> 7) & 0x01010101u;
+        bits |= ((fr * 0x01020408u) >> 24 & 0xFu) << (4 * u);
+    }
+    return bits;
+}
+
+template <int WPR, bool GEN>
+__global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a) {
+    constexpr int P = 32 * WPR;                 // padded grid side = threads per CTA
+    constexpr int NT = P, NW = WPR;
+    constexpr int PLANE_WORDS = P * WPR;        // one bit-plane of the padded grid, [row][WPR]
+    extern __shared__ __align__(16) uint32_t pls[];              // planes 1..NPSL, then visited, free: [k-1][row][WPR]
+    __shared__ __align__(16) uint32_t bnd[2][NW + 2][2][WPR];    // frontier rows at warp boundaries (double buffered)
+    __shared__ LargeInfo info;
+    uint32_t *const pv = pls + NPSL * PLANE_WORDS;               // reached free cells (post-BFS)
+    uint32_t *const pf = pls + (NPSL + 1) * PLANE_WORDS;         // free cells (post-BFS)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = tid;
     const int G = a.G;
-    const int wpr = G >> 5;              // words per row
-    const int nw = G * wpr;              // words per mask
-    uint32_t *A = sm, *F0 = sm + nw, *F1 = sm + 2 * nw, *FR = sm + 3 * nw;
-    const int tid = threadIdx.x;
     const int count = a.count_ptr ? static_cast<int>(*a.count_ptr) : a.count;
+    uint32_t *hi = a.hi_scratch + static_cast<size_t>(blockIdx.x) * (NPGL * PLANE_WORDS);   // planes NPSL+1..15
     const size_t cells = static_cast<size_t>(G) * G;
+    const uint32_t neg1 = a.neg1;
+    const uint32_t m_up = lane == 0 ? 0u : a.one, m_dn = lane == 31 ? 0u : a.one;   // IMAD masks of the shuffled rows
+    auto plane_ptr = [&](int k) -> uint32_t * {      // k >= 1
+        return k <= NPSL ? &pls[((k - 1) * P + row) * WPR] : &hi[((k - 1 - NPSL) * P + row) * WPR];
+    };
+
+    for (int i = tid; i < 2 * (NW + 2) * 2 * WPR; i += NT) (&bnd[0][0][0][0])[i] = 0;     // ghost entries stay zero
+    __syncthreads();
 
     for (int item = blockIdx.x; item < count; item += gridDim.x) {
+        // ---- 0. item parameters ------------------------------------------------------------------------
         if (tid == 0) {
             const uint32_t env = a.env_idx ? a.env_idx[item] : static_cast<uint32_t>(item);
             if (GEN) {
                 const uint32_t episode = a.episode ? a.episode[item] : a.episode_const;
-                sh.plane = static_cast<unsigned long long>(episode % a.S) * a.N + env;
-                sh.key = scenario_key(a.seed, a.env_id_base + env, episode);
-                sh.sp = sample_scenario(sh.key, G, a.goal_mode);
-                store_scenario_record(a.scen_out + sh.plane * SC_WORDS, sh.sp, sh.key);
-                sh.gi = sh.sp.gi; sh.gj = sh.sp.gj;
+                info.plane = static_cast<unsigned long long>(episode % a.S) * a.N + env;
+                info.key = scenario_key(a.seed, a.env_id_base + env, episode);
+                info.sp = sample_scenario(info.key, G, a.goal_mode);
+                store_scenario_record(a.scen_out + info.plane * SC_WORDS, info.sp, info.key);
+                info.gi = info.sp.gi; info.gj = info.sp.gj;
             } else if (a.slot_mode) {
-                sh.plane = static_cast<unsigned long long>((a.episode ? a.episode[item] : a.episode_const) % a.S) * a.N + env;
-                sh.gi = static_cast<int>(a.scen[sh.plane * SC_WORDS + SC_GI]);
-                sh.gj = static_cast<int>(a.scen[sh.plane * SC_WORDS + SC_GJ]);
+                info.plane = static_cast<unsigned long long>((a.episode ? a.episode[item] : a.episode_const) % a.S) * a.N + env;
+                info.gi = static_cast<int>(a.scen[info.plane * SC_WORDS + SC_GI]);
+                info.gj = static_cast<int>(a.scen[info.plane * SC_WORDS + SC_GJ]);
             } else {
-                sh.plane = static_cast<unsigned long long>(item);
-                sh.gi = a.goal_cells[2 * item];
-                sh.gj = a.goal_cells[2 * item + 1];
+                info.plane = static_cast<unsigned long long>(item);
+                info.gi = a.goal_cells[2 * item];
+                info.gj = a.goal_cells[2 * item + 1];
             }
         }
         __syncthreads();
-        const size_t plane = static_cast<size_t>(sh.plane);
-        const int gi = sh.gi, gj = sh.gj;
-        int32_t *cost = a.cost + plane * cells;
-        uint8_t *flow = a.flow + plane * cells;
+        const size_t plane = static_cast<size_t>(info.plane);
+        const int gi = info.gi, gj = info.gj;
 
-        // ---- free mask (generated or packed from the occupancy bytes), cost plane pre-filled with INF ----
-        for (int w = tid; w < nw; w += LARGE_THREADS) {
-            const int R = w / wpr, wc = w - R * wpr;
-            uint32_t fr;
-            if (GEN) {
-                fr = scenario_free_word(sh.key, R, 32 * wc, G, a.block_shift, a.p_thresh, sh.sp);
-            } else {
-                const uint4 *src = reinterpret_cast<const uint4 *>(a.occ + plane * cells + static_cast<size_t>(R) * G + 32 * wc);
-                fr = 0;
+        // ---- 1. free-cell mask of this thread's row ----------------------------------------------------
+        uint32_t FR[WPR];
+        if (GEN) {
+#pragma unroll 1
+            for (int w = 0; w < WPR; ++w) {
+                const uint32_t v = scenario_free_word(info.key, row, 32 * w, G, a.block_shift, a.p_thresh, info.sp);
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const uint4 v = __ldg(src + q);
-                    const uint32_t x4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint32_t x = x4[u];
-                        const uint32_t nz = (x | ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu)) & 0x80808080u;
-                        const uint32_t f = (~nz >> 7) & 0x01010101u;
-                        fr |= ((f * 0x01020408u) >> 24 & 0xFu) << (16 * q + 4 * u);
-                    }
-                }
+                for (int u = 0; u < WPR; ++u)
+                    if (u == w) FR[u] = v;     // static register index
             }
-            FR[w] = fr; A[w] = fr; F0[w] = 0; F1[w] = 0;
+        } else {
+            // the thread's row is G contiguous bytes (16-byte aligned: G % 32 == 0): two 16-byte loads per mask word
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.occ + plane * cells + static_cast<size_t>(row) * G);
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) {
+                uint32_t v = 0;
+                if (row < G && 32 * w < G) v = pack16(__ldg(src + 2 * w)) | (pack16(__ldg(src + 2 * w + 1)) << 16);
+                FR[w] = v;
+            }
         }
+
+        Row<WPR>::st(&pf[row * WPR], FR);     // kept for the post-BFS phases; the loop below only needs `avail`
+
+        // ---- 2. bit-parallel wavefront -----------------------------------------------------------------
+        uint32_t A[WPR], F[WPR], G0[WPR];
         {
-            int4 *c4 = reinterpret_cast<int4 *>(cost);
-            const int4 inf = make_int4(COST_INF, COST_INF, COST_INF, COST_INF);
-            for (size_t c = tid; c < cells / 4; c += LARGE_THREADS) c4[c] = inf;
+            uint32_t z[WPR];
+            const int gw = gj >> 5;
+            const uint32_t bit = (row == gi && gj >= 0 && gj < G) ? (1u << (gj & 31)) : 0u;
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) {
+                z[w] = 0; G0[w] = 0;
+                const uint32_t m = (w == gw) ? (bit & FR[w]) : 0u;
+                F[w] = m;
+                A[w] = FR[w] ^ m;
+            }
+#pragma unroll
+            for (int k = 1; k <= NPSL; ++k) Row<WPR>::st(&pls[((k - 1) * P + row) * WPR], z);
         }
+        if (lane == 0) Row<WPR>::st(bnd[0][warp + 1][0], F);
+        if (lane == 31) Row<WPR>::st(bnd[0][warp + 1][1], F);
         __syncthreads();
-        if (tid == 0 && gi >= 0 && gj >= 0 && gi < G && gj < G) {
-            const int w = gi * wpr + (gj >> 5);
-            const uint32_t m = (1u << (gj & 31)) & A[w];
-            if (m) { F0[w] = m; A[w] &= ~m; cost[static_cast<size_t>(gi) * G + gj] = 0; }
+        int pb = 0;
+        uint32_t L = 1;
+        for (;; ++L) {
+            // Gray bit-plane update: cells with cost >= L flip Gray bit ctz(L)
+            const int k = __ffs(L) - 1;
+            if (k == 0) {
+#pragma unroll
+                for (int w = 0; w < WPR; ++w) G0[w] ^= A[w];
+            } else if (k <= NPSL) {
+                uint32_t v[WPR];
+                uint32_t *p = &pls[((k - 1) * P + row) * WPR];
+                Row<WPR>::ld(p, v);
+#pragma unroll
+                for (int w = 0; w < WPR; ++w) v[w] ^= A[w];
+                Row<WPR>::st(p, v);
+            } else {
+                const bool first = L == (1u << k);
+                uint32_t *p = &hi[((k - 1 - NPSL) * P + row) * WPR];
+                uint32_t v[WPR];
+                if (first) {
+#pragma unroll
+                    for (int w = 0; w < WPR; ++w) v[w] = A[w];
+                } else {
+                    Row<WPR>::ld(p, v);
+#pragma unroll
+                    for (int w = 0; w < WPR; ++w) v[w] ^= A[w];
+                }
+                Row<WPR>::st(p, v);
+            }
+            // frontier rows above / below: neighbouring lanes by shuffle; lanes 0 / 31 take the neighbouring warp's row from
+            // `bnd` (vector loads, zero in every other lane) and the two are merged with an IMAD, so the loop stays
+            // branch-free and off the ALU pipe.  The words are walked in place: shuffles and carries use the old F[w].
+            uint32_t bu[WPR], bd[WPR];
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) { bu[w] = 0; bd[w] = 0; }
+            if (lane == 0) Row<WPR>::ld(bnd[pb][warp][1], bu);
+            if (lane == 31) Row<WPR>::ld(bnd[pb][warp + 2][0], bd);
+            uint32_t any = 0, f_prev = 0;
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) {
+                const uint32_t f_cur = F[w], f_next = w + 1 < WPR ? F[w + 1] : 0u;
+                uint32_t up, dn;
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(up) : "r"(__shfl_up_sync(FULL, f_cur, 1)), "r"(m_up), "r"(bu[w]));
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(dn) : "r"(__shfl_down_sync(FULL, f_cur, 1)), "r"(m_dn), "r"(bd[w]));
+                const uint32_t lo = w > 0 ? __funnelshift_l(f_prev, f_cur, 1) : f_cur << 1;
+                const uint32_t hv = w + 1 < WPR ? __funnelshift_r(f_cur, f_next, 1) : f_cur >> 1;
+                const uint32_t n = (lo | hv | up | dn) & A[w];
+                any |= n;
+                A[w] = sub_on_fma(A[w], n, neg1);
+                F[w] = n;
+                f_prev = f_cur;
+            }
+            if (lane == 0) Row<WPR>::st(bnd[pb ^ 1][warp + 1][0], F);
+            if (lane == 31) Row<WPR>::st(bnd[pb ^ 1][warp + 1][1], F);
+            if (!__syncthreads_or(any != 0)) break;
+            pb ^= 1;
+        }
+        const uint32_t Lmax = L - 1;                       // deepest level that reached a cell
+        const int kmax = 32 - __clz(Lmax);                  // number of significant cost bits (<= NPMAX)
+
+        // ---- 3. Gray -> binary of this thread's row (planes stay where they live); visited / free rows to shared memory ----
+        uint32_t B0[WPR];
+        {
+            uint32_t acc[WPR];
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) acc[w] = 0;
+#pragma unroll 1
+            for (int k = kmax - 1; k >= 1; --k) {
+                uint32_t *p = plane_ptr(k);
+                uint32_t v[WPR];
+                Row<WPR>::ld(p, v);
+#pragma unroll
+                for (int w = 0; w < WPR; ++w) { acc[w] ^= v[w]; v[w] = acc[w]; }
+                Row<WPR>::st(p, v);
+            }
+            uint32_t V[WPR];
+            Row<WPR>::ld(&pf[row * WPR], V);
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) { B0[w] = kmax > 0 ? (acc[w] ^ G0[w]) : 0u; V[w] &= ~A[w]; }
+            Row<WPR>::st(&pv[row * WPR], V);
         }
         __syncthreads();
 
-        // ---- level-synchronous bit-parallel wavefront ----------------------------------------------
-        uint32_t *F = F0, *Fn = F1;
-        for (int L = 1;; ++L) {
-            int any = 0;
-            for (int w = tid; w < nw; w += LARGE_THREADS) {
-                const int R = w / wpr, wc = w - R * wpr;
-                const uint32_t c = F[w];
-                const uint32_t lw = wc > 0 ? F[w - 1] : 0u, rw = wc < wpr - 1 ? F[w + 1] : 0u;
-                const uint32_t up = R > 0 ? F[w - wpr] : 0u, dn = R < G - 1 ? F[w + wpr] : 0u;
-                uint32_t n = 0;
-                if (c | lw | rw | up | dn) n = ((c << 1) | (lw >> 31) | (c >> 1) | (rw << 31) | up | dn) & A[w];
-                Fn[w] = n;
-                if (n) {
-                    A[w] &= ~n;
-                    any = 1;
-                    int32_t *dst = cost + static_cast<size_t>(R) * G + 32 * wc;
-                    uint32_t m = n;
-                    while (m) {
-                        const int b = __ffs(m) - 1;
-                        dst[b] = L;
-                        m &= m - 1;
+        // ---- 4. flow direction, bit-parallel (SPEC.md §4 F2), and the flow image ------------------------
+        // Everything but this row's cost bit 0 is read from shared memory, word by word (rows R-1 "u" = west, R+1 "d" = east).
+        {
+            const uint32_t *p1 = pls, *p2 = pls + PLANE_WORDS;       // binary cost bits 1 and 2
+            const bool has1 = kmax > 1, has2 = kmax > 2;
+            auto ldw = [&](const uint32_t *pl_, bool on, int r, int w) -> uint32_t {
+                return (on && r >= 0 && r < P && w >= 0 && w < WPR) ? pl_[r * WPR + w] : 0u;
+            };
+            // value of the cell at column+1 / column-1 aligned to word w of row r
+            auto hiw = [&](const uint32_t *pl_, bool on, int r, int w) { return (ldw(pl_, on, r, w) >> 1) | (ldw(pl_, on, r, w + 1) << 31); };
+            auto low = [&](const uint32_t *pl_, bool on, int r, int w) { return (ldw(pl_, on, r, w) << 1) | (ldw(pl_, on, r, w - 1) >> 31); };
+            uint8_t *flow = a.flow + plane * cells + static_cast<size_t>(row) * G;
+#pragma unroll 1
+            for (int w = 0; w < WPR; ++w) {
+                if (row >= G || 32 * w >= G) break;
+                uint32_t b0 = 0;
+#pragma unroll
+                for (int u = 0; u < WPR; ++u)
+                    if (u == w) b0 = B0[u];
+                const int ru = row - 1, rd = row + 1;
+                const uint32_t b1c = ldw(p1, has1, row, w), b2c = ldw(p2, has2, row, w);
+                const uint32_t own = ldw(pv, true, row, w);
+                const uint32_t fc = ldw(pf, true, row, w);
+                const uint32_t t = b1c ^ ~b0;    // bit 1 of (cost-1)
+                const uint32_t u2 = b2c ^ ~b1c;  // bit 2 of (cost-2)
+                // orthogonal neighbours one level lower (codes 0 E, 2 N, 4 W, 6 S)
+                const uint32_t lE = own & ldw(pv, true, rd, w) & ~(ldw(p1, has1, rd, w) ^ t);
+                const uint32_t lW = own & ldw(pv, true, ru, w) & ~(ldw(p1, has1, ru, w) ^ t);
+                const uint32_t lN = own & hiw(pv, true, row, w) & ~(hiw(p1, has1, row, w) ^ t);
+                const uint32_t lS = own & low(pv, true, row, w) & ~(low(p1, has1, row, w) ^ t);
+                // admissible diagonals two levels lower (codes 1 NE, 3 NW, 5 SW, 7 SE)
+                const uint32_t fE = ldw(pf, true, rd, w), fW = ldw(pf, true, ru, w), fN = hiw(pf, true, row, w), fS = low(pf, true, row, w);
+                const uint32_t lNE = own & hiw(pf, true, rd, w) & fE & fN & (hiw(p1, has1, rd, w) ^ b1c) & ~(hiw(p2, has2, rd, w) ^ u2);
+                const uint32_t lNW = own & hiw(pf, true, ru, w) & fW & fN & (hiw(p1, has1, ru, w) ^ b1c) & ~(hiw(p2, has2, ru, w) ^ u2);
+                const uint32_t lSW = own & low(pf, true, ru, w) & fW & fS & (low(p1, has1, ru, w) ^ b1c) & ~(low(p2, has2, ru, w) ^ u2);
+                const uint32_t lSE = own & low(pf, true, rd, w) & fE & fS & (low(p1, has1, rd, w) ^ b1c) & ~(low(p2, has2, rd, w) ^ u2);
+                const uint32_t anyD = lNE | lNW | lSW | lSE;
+                const uint32_t m0 = (anyD & lNE) | (~anyD & lE);
+                const uint32_t m1 = (anyD & lNW) | (~anyD & lN);
+                const uint32_t m2 = (anyD & lSW) | (~anyD & lW);
+                const uint32_t m3 = (anyD & lSE) | (~anyD & lS);
+                const uint32_t d1 = ~m0 & (m1 | (~m2 & m3));
+                const uint32_t d2 = ~m0 & ~m1 & (m2 | m3);
+                const uint32_t d3 = ~(m0 | m1 | m2 | m3);
+                uint32_t out[8];
+                flow_bytes32(anyD, d1, d2, d3, ~fc, out);
+                uint4 *dst = reinterpret_cast<uint4 *>(flow + 32 * w);
+                dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+                dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+            }
+        }
+
+        // ---- 5. integration field: bit-planes -> int32 (INF for cells not reached) -----------------------
+        // One mask word is one 128-byte line of cost: the thread writes it with eight 16-byte stores.
+        if (row < G) {
+            int32_t *cost = a.cost + plane * cells + static_cast<size_t>(row) * G;
+#pragma unroll 1
+            for (int w = 0; w < WPR; ++w) {
+                if (32 * w >= G) break;
+                uint32_t bw[NPMAX];
+#pragma unroll
+                for (int k = 0; k < NPMAX; ++k) bw[k] = 0;
+                const uint32_t vis = pv[row * WPR + w];
+#pragma unroll
+                for (int u = 0; u < WPR; ++u)
+                    if (u == w) bw[0] = B0[u];
+#pragma unroll
+                for (int k = 1; k < NPMAX; ++k)
+                    if (k < kmax) bw[k] = plane_ptr(k)[w];
+                uint32_t lo8[8], hi8[8], top8[8];   // cost bits 0-7 / 8-15 / 16-17 of the 32 cells, 4 cells per word
+                {
+                    uint32_t tl[4], th[4];
+                    bytes4x4(bw[0], bw[1], bw[2], bw[3], tl);
+                    bytes4x4(bw[4], bw[5], bw[6], bw[7], th);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        uint32_t x = tl[b], y = th[b];
+                        transpose8(x, y);
+                        lo8[2 * b] = x; lo8[2 * b + 1] = y;
                     }
                 }
+#pragma unroll
+                for (int b = 0; b < 8; ++b) { hi8[b] = 0; top8[b] = 0; }
+                if (kmax > 8) {
+                    uint32_t tl[4], th[4];
+                    bytes4x4(bw[8], bw[9], bw[10], bw[11], tl);
+                    bytes4x4(bw[12], bw[13], bw[14], bw[15], th);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        uint32_t x = tl[b], y = th[b];
+                        transpose8(x, y);
+                        hi8[2 * b] = x; hi8[2 * b + 1] = y;
+                    }
+                }
+                if (kmax > 16) {
+                    uint32_t tl[4];
+                    bytes4x4(bw[16], bw[17], 0u, 0u, tl);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        uint32_t x = tl[b], y = 0u;
+                        transpose8(x, y);
+                        top8[2 * b] = x; top8[2 * b + 1] = y;
+                    }
+                }
+                int4 *dst = reinterpret_cast<int4 *>(cost + 32 * w);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t l4 = lo8[q], h4 = hi8[q], t4 = top8[q], vb = vis >> (4 * q);
+                    int4 c;
+                    c.x = (vb & 1u) ? static_cast<int>((l4 & 0xFFu) | ((h4 & 0xFFu) << 8) | ((t4 & 0xFFu) << 16)) : COST_INF;
+                    c.y = (vb & 2u) ? static_cast<int>(((l4 >> 8) & 0xFFu) | (((h4 >> 8) & 0xFFu) << 8) | (((t4 >> 8) & 0xFFu) << 16)) : COST_INF;
+                    c.z = (vb & 4u) ? static_cast<int>(((l4 >> 16) & 0xFFu) | (((h4 >> 16) & 0xFFu) << 8) | (((t4 >> 16) & 0xFFu) << 16)) : COST_INF;
+                    c.w = (vb & 8u) ? static_cast<int>((l4 >> 24) | ((h4 >> 24) << 8) | ((t4 >> 24) << 16)) : COST_INF;
+                    dst[q] = c;
+                }
             }
-            if (!__syncthreads_or(any)) break;
-            uint32_t *t = F; F = Fn; Fn = t;
         }
-        __syncthreads();   // cost stores of every thread are visible to the CTA
-
-        // ---- flow direction (explicit 8-neighbour scan on the cost plane) and flow image -----------
-        for (size_t c = tid; c < cells; c += LARGE_THREADS) {
-            const int i = static_cast<int>(c / G), j = static_cast<int>(c - static_cast<size_t>(i) * G);
-            const bool occupied = !((FR[i * wpr + (j >> 5)] >> (j & 31)) & 1u);
-            uint32_t d = 8;
-            const int own = cost[c];
-            if (own != COST_INF) {
-                auto at = [&](int ii, int jj) -> int {
-                    return (ii < 0 || jj < 0 || ii >= G || jj >= G) ? COST_INF : cost[static_cast<size_t>(ii) * G + jj];
-                };
-                const int cE = at(i + 1, j), cN = at(i, j + 1), cW = at(i - 1, j), cS = at(i, j - 1);
-                int best = own;
-                // scan order E, NE, N, NW, W, SW, S, SE with strict '<'; a diagonal needs both side cells free
-                // (a free side cell next to a reached cell is reached, so "free" == "cost != INF" here)
-                if (cE < best) { best = cE; d = 0; }
-                if (cE != COST_INF && cN != COST_INF) { const int v = at(i + 1, j + 1); if (v < best) { best = v; d = 1; } }
-                if (cN < best) { best = cN; d = 2; }
-                if (cW != COST_INF && cN != COST_INF) { const int v = at(i - 1, j + 1); if (v < best) { best = v; d = 3; } }
-                if (cW < best) { best = cW; d = 4; }
-                if (cW != COST_INF && cS != COST_INF) { const int v = at(i - 1, j - 1); if (v < best) { best = v; d = 5; } }
-                if (cS < best) { best = cS; d = 6; }
-                if (cE != COST_INF && cS != COST_INF) { const int v = at(i + 1, j - 1); if (v < best) { best = v; d = 7; } }
-            }
-            flow[c] = occupied ? 255 : static_cast<uint8_t>(d * 28);
-        }
-        __syncthreads();
+        __syncthreads();   // the planes and `bnd` are reused by the next grid
     }
 
     if (a.ticket && tid == 0) {
@@ -165,33 +350,51 @@ __global__ void __launch_bounds__(LARGE_THREADS) flow_field_cta_kernel(FlowArgs 
     }
 }
 
-size_t large_smem_bytes(int G) { return static_cast<size_t>(4) * G * (G >> 5) * sizeof(uint32_t); }
+int large_wpr(int G) { return G <= 256 ? 8 : 16; }
+size_t large_smem_bytes(int G) {
+    const int wpr = large_wpr(G);
+    return static_cast<size_t>(NSM) * 32 * wpr * wpr * sizeof(uint32_t);
+}
 
 }  // namespace
 
 bool flow_field_large_supported(int G) { return G > 128 && G <= 512 && (G % 32) == 0; }
 
+size_t flow_field_large_scratch_words(int G) {
+    const int wpr = large_wpr(G);
+    return static_cast<size_t>(NPGL) * 32 * wpr * wpr;
+}
+
 int flow_field_large_max_grid(int G) {
-    int per_sm = static_cast<int>((227 * 1024) / (large_smem_bytes(G) + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 2) per_sm = 2;   // 1024 threads per CTA
+    if (large_wpr(G) == 16) return 148;                       // 512 threads, 160 KB of planes: one CTA per SM
+    int per_sm = static_cast<int>((227 * 1024) / (large_smem_bytes(G) + 8 * 1024));
+    if (per_sm > 4) per_sm = 4;
     return 148 * per_sm;
 }
 
-cudaError_t launch_flow_field_large(const FlowArgs &a, int grid, cudaStream_t st) {
+cudaError_t launch_flow_field_large(const FlowArgs &a_in, int grid, cudaStream_t st) {
     if (grid <= 0) return cudaSuccess;
-    if (!a.cost) return cudaErrorInvalidValue;   // the direction pass reads the cost plane
+    if (!a_in.cost) return cudaErrorInvalidValue;   // the large-map kernel always writes the integration field
+    FlowArgs a = a_in;
+    a.neg1 = 0xFFFFFFFFu;
+    a.one = 1u;
     const size_t smem = large_smem_bytes(a.G);
     static bool configured = false;
     if (!configured) {
-        cudaError_t ce = cudaFuncSetAttribute(flow_field_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (ce == cudaSuccess)
-            ce = cudaFuncSetAttribute(flow_field_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t ce = cudaFuncSetAttribute(flow_field_rows_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(flow_field_rows_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(flow_field_rows_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(flow_field_rows_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (ce != cudaSuccess) return ce;
         configured = true;
     }
-    if (a.generate) flow_field_cta_kernel<true><<<grid, LARGE_THREADS, smem, st>>>(a);
-    else flow_field_cta_kernel<false><<<grid, LARGE_THREADS, smem, st>>>(a);
+    if (large_wpr(a.G) == 16) {
+        if (a.generate) flow_field_rows_kernel<16, true><<<grid, 512, smem, st>>>(a);
+        else flow_field_rows_kernel<16, false><<<grid, 512, smem, st>>>(a);
+    } else {
+        if (a.generate) flow_field_rows_kernel<8, true><<<grid, 256, smem, st>>>(a);
+        else flow_field_rows_kernel<8, false><<<grid, 256, smem, st>>>(a);
+    }
     return cudaGetLastError();
 }
 
