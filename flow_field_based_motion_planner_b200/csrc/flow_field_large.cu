@@ -4,8 +4,8 @@
 // CTA of P threads (P = 256 or 512 padded rows) owns the grid: thread t holds row t of the avail / frontier masks as WPR
 // 32-bit words in REGISTERS (16 words at G = 512), exactly the per-lane layout of the small kernel with one row per lane,
 // and the same ALU-lean wavefront step (funnel shifts + two LOP3 per word, avail update on the FMA pipe).  Rows above /
-// below are warp shuffles; the rows at warp boundaries are exchanged through a double-buffered shared-memory array, and
-// one __syncthreads_or per level both publishes them and tests convergence.  BFS levels are recorded as Gray-code
+// below come from a double-buffered shared-memory frontier buffer (chunk-major, conflict-free 16-byte accesses), and one
+// __syncthreads_or per level both orders that exchange and tests convergence.  BFS levels are recorded as Gray-code
 // bit-planes: plane 0 in registers, planes 1..NPSL in shared memory, the rest (touched every 2^(k+1) levels) in a per-CTA
 // global scratch that stays in L2.  Afterwards each thread un-Grays its row, evaluates the 8-neighbour argmin bit-parallel
 // (neighbour rows from the shared-memory planes), and writes its row of the flow image and of the int32 integration field:
@@ -46,28 +46,42 @@ __device__ __forceinline__ uint32_t pack16(const uint4 q) {
 template <int WPR, bool GEN>
 __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a) {
     constexpr int P = 32 * WPR;                 // padded grid side = threads per CTA
-    constexpr int NT = P, NW = WPR;
-    constexpr int PLANE_WORDS = P * WPR;        // one bit-plane of the padded grid, [row][WPR]
-    extern __shared__ __align__(16) uint32_t pls[];              // planes 1..NPSL, then visited, free: [k-1][row][WPR]
-    __shared__ __align__(16) uint32_t bnd[2][NW + 2][2][WPR];    // frontier rows at warp boundaries (double buffered)
+    constexpr int NQ = WPR / 4;                 // 16-byte chunks per row
+    constexpr int PLANE_WORDS = P * WPR;        // one bit-plane of the padded grid
+    constexpr int FBUF_WORDS = (P + 2) * WPR;   // a frontier buffer: rows -1..P (the two ghost rows stay zero)
+    // Shared-memory planes are CHUNK-MAJOR, word (r, w) at ((w / 4) * rows + r) * 4 + w % 4, so that the 16-byte accesses of
+    // consecutive lanes (consecutive rows) are consecutive in memory (a row-major layout would be a 4-way bank conflict).
+    //   [0, NPSL)            Gray planes 1..NPSL
+    //   then two frontier buffers (all rows, double buffered) during the BFS; afterwards the same storage holds the
+    //   reached (pv) and free (pf) masks for the direction pass.
+    extern __shared__ __align__(16) uint32_t pls[];
     __shared__ LargeInfo info;
-    uint32_t *const pv = pls + NPSL * PLANE_WORDS;               // reached free cells (post-BFS)
-    uint32_t *const pf = pls + (NPSL + 1) * PLANE_WORDS;         // free cells (post-BFS)
+    uint32_t *const fb0 = pls + NPSL * PLANE_WORDS;
+    uint32_t *const fb1 = fb0 + FBUF_WORDS;
+    uint32_t *const pv = fb0, *const pf = fb1;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int row = tid;
     const int G = a.G;
     const int count = a.count_ptr ? static_cast<int>(*a.count_ptr) : a.count;
-    uint32_t *hi = a.hi_scratch + static_cast<size_t>(blockIdx.x) * (NPGL * PLANE_WORDS);   // planes NPSL+1..15
+    // per-CTA global scratch (L2): Gray planes NPSL+1..NPMAX-1 and the free mask, row-major [row][WPR]
+    uint32_t *hi = a.hi_scratch + static_cast<size_t>(blockIdx.x) * ((NPGL + 1) * PLANE_WORDS);
+    uint32_t *const free_g = hi + NPGL * PLANE_WORDS + row * WPR;
     const size_t cells = static_cast<size_t>(G) * G;
     const uint32_t neg1 = a.neg1;
-    const uint32_t m_up = lane == 0 ? 0u : a.one, m_dn = lane == 31 ? 0u : a.one;   // IMAD masks of the shuffled rows
-    auto plane_ptr = [&](int k) -> uint32_t * {      // k >= 1
-        return k <= NPSL ? &pls[((k - 1) * P + row) * WPR] : &hi[((k - 1 - NPSL) * P + row) * WPR];
+    auto gl_plane = [&](int k) -> uint32_t * { return &hi[((k - 1 - NPSL) * P + row) * WPR]; };           // k > NPSL, own row
+    auto sm_ld = [&](const uint32_t *base, int rows, int r, uint32_t (&v)[WPR]) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const uint4 t = *reinterpret_cast<const uint4 *>(base + (q * rows + r) * 4);
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
     };
-
-    for (int i = tid; i < 2 * (NW + 2) * 2 * WPR; i += NT) (&bnd[0][0][0][0])[i] = 0;     // ghost entries stay zero
-    __syncthreads();
+    auto sm_st = [&](uint32_t *base, int rows, int r, const uint32_t (&v)[WPR]) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+            *reinterpret_cast<uint4 *>(base + (q * rows + r) * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    };
 
     for (int item = blockIdx.x; item < count; item += gridDim.x) {
         // ---- 0. item parameters ------------------------------------------------------------------------
@@ -94,15 +108,15 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
         const size_t plane = static_cast<size_t>(info.plane);
         const int gi = info.gi, gj = info.gj;
 
-        // ---- 1. free-cell mask of this thread's row ----------------------------------------------------
-        uint32_t FR[WPR];
+        // ---- 1. free-cell mask of this thread's row; frontier seed; zeroed planes -------------------------
+        uint32_t A[WPR], F[WPR], G0[WPR];
         if (GEN) {
 #pragma unroll 1
             for (int w = 0; w < WPR; ++w) {
                 const uint32_t v = scenario_free_word(info.key, row, 32 * w, G, a.block_shift, a.p_thresh, info.sp);
 #pragma unroll
                 for (int u = 0; u < WPR; ++u)
-                    if (u == w) FR[u] = v;     // static register index
+                    if (u == w) A[u] = v;     // static register index
             }
         } else {
             // the thread's row is G contiguous bytes (16-byte aligned: G % 32 == 0): two 16-byte loads per mask word
@@ -111,14 +125,10 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
             for (int w = 0; w < WPR; ++w) {
                 uint32_t v = 0;
                 if (row < G && 32 * w < G) v = pack16(__ldg(src + 2 * w)) | (pack16(__ldg(src + 2 * w + 1)) << 16);
-                FR[w] = v;
+                A[w] = v;
             }
         }
-
-        Row<WPR>::st(&pf[row * WPR], FR);     // kept for the post-BFS phases; the loop below only needs `avail`
-
-        // ---- 2. bit-parallel wavefront -----------------------------------------------------------------
-        uint32_t A[WPR], F[WPR], G0[WPR];
+        Row<WPR>::st(free_g, A);              // kept for the post-BFS phases; the loop below only needs `avail`
         {
             uint32_t z[WPR];
             const int gw = gj >> 5;
@@ -126,17 +136,26 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
 #pragma unroll
             for (int w = 0; w < WPR; ++w) {
                 z[w] = 0; G0[w] = 0;
-                const uint32_t m = (w == gw) ? (bit & FR[w]) : 0u;
+                const uint32_t m = (w == gw) ? (bit & A[w]) : 0u;
                 F[w] = m;
-                A[w] = FR[w] ^ m;
+                A[w] ^= m;
             }
 #pragma unroll
-            for (int k = 1; k <= NPSL; ++k) Row<WPR>::st(&pls[((k - 1) * P + row) * WPR], z);
+            for (int k = 0; k < NPSL; ++k) sm_st(pls + k * PLANE_WORDS, P, row, z);
+            if (tid < 2) {            // ghost rows -1 and P of both frontier buffers
+                sm_st(fb0, P + 2, tid * (P + 1), z);
+                sm_st(fb1, P + 2, tid * (P + 1), z);
+            }
         }
-        if (lane == 0) Row<WPR>::st(bnd[0][warp + 1][0], F);
-        if (lane == 31) Row<WPR>::st(bnd[0][warp + 1][1], F);
+        sm_st(fb0, P + 2, row + 1, F);
         __syncthreads();
-        int pb = 0;
+
+        // ---- 2. bit-parallel wavefront -----------------------------------------------------------------
+        // Every level: the rows above / below come from the frontier buffer published by the previous level (two vector
+        // loads per 4 words, conflict-free), the words are walked in place (funnel shifts use the old F[w]), the new
+        // frontier row is published into the other buffer, and one __syncthreads_or both orders the exchange and tests
+        // convergence.
+        uint32_t *fcur = fb0, *fnext = fb1;
         uint32_t L = 1;
         for (;; ++L) {
             // Gray bit-plane update: cells with cost >= L flip Gray bit ctz(L)
@@ -146,14 +165,14 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
                 for (int w = 0; w < WPR; ++w) G0[w] ^= A[w];
             } else if (k <= NPSL) {
                 uint32_t v[WPR];
-                uint32_t *p = &pls[((k - 1) * P + row) * WPR];
-                Row<WPR>::ld(p, v);
+                uint32_t *p = pls + (k - 1) * PLANE_WORDS;
+                sm_ld(p, P, row, v);
 #pragma unroll
                 for (int w = 0; w < WPR; ++w) v[w] ^= A[w];
-                Row<WPR>::st(p, v);
+                sm_st(p, P, row, v);
             } else {
                 const bool first = L == (1u << k);
-                uint32_t *p = &hi[((k - 1 - NPSL) * P + row) * WPR];
+                uint32_t *p = gl_plane(k);
                 uint32_t v[WPR];
                 if (first) {
 #pragma unroll
@@ -165,57 +184,58 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
                 }
                 Row<WPR>::st(p, v);
             }
-            // frontier rows above / below: neighbouring lanes by shuffle; lanes 0 / 31 take the neighbouring warp's row from
-            // `bnd` (vector loads, zero in every other lane) and the two are merged with an IMAD, so the loop stays
-            // branch-free and off the ALU pipe.  The words are walked in place: shuffles and carries use the old F[w].
-            uint32_t bu[WPR], bd[WPR];
-#pragma unroll
-            for (int w = 0; w < WPR; ++w) { bu[w] = 0; bd[w] = 0; }
-            if (lane == 0) Row<WPR>::ld(bnd[pb][warp][1], bu);
-            if (lane == 31) Row<WPR>::ld(bnd[pb][warp + 2][0], bd);
+            uint32_t up[WPR], dn[WPR];
+            sm_ld(fcur, P + 2, row, up);          // buffer row r+1 holds grid row r: row - 1 -> index row
+            sm_ld(fcur, P + 2, row + 2, dn);
             uint32_t any = 0, f_prev = 0;
 #pragma unroll
             for (int w = 0; w < WPR; ++w) {
                 const uint32_t f_cur = F[w], f_next = w + 1 < WPR ? F[w + 1] : 0u;
-                uint32_t up, dn;
-                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(up) : "r"(__shfl_up_sync(FULL, f_cur, 1)), "r"(m_up), "r"(bu[w]));
-                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(dn) : "r"(__shfl_down_sync(FULL, f_cur, 1)), "r"(m_dn), "r"(bd[w]));
                 const uint32_t lo = w > 0 ? __funnelshift_l(f_prev, f_cur, 1) : f_cur << 1;
                 const uint32_t hv = w + 1 < WPR ? __funnelshift_r(f_cur, f_next, 1) : f_cur >> 1;
-                const uint32_t n = (lo | hv | up | dn) & A[w];
+                const uint32_t n = (lo | hv | up[w] | dn[w]) & A[w];
                 any |= n;
                 A[w] = sub_on_fma(A[w], n, neg1);
                 F[w] = n;
                 f_prev = f_cur;
             }
-            if (lane == 0) Row<WPR>::st(bnd[pb ^ 1][warp + 1][0], F);
-            if (lane == 31) Row<WPR>::st(bnd[pb ^ 1][warp + 1][1], F);
+            sm_st(fnext, P + 2, row + 1, F);
             if (!__syncthreads_or(any != 0)) break;
-            pb ^= 1;
+            uint32_t *t = fcur; fcur = fnext; fnext = t;
         }
         const uint32_t Lmax = L - 1;                       // deepest level that reached a cell
         const int kmax = 32 - __clz(Lmax);                  // number of significant cost bits (<= NPMAX)
 
-        // ---- 3. Gray -> binary of this thread's row (planes stay where they live); visited / free rows to shared memory ----
+        // ---- 3. Gray -> binary of this thread's row (planes stay where they live); reached / free rows to shared memory ----
         uint32_t B0[WPR];
         {
             uint32_t acc[WPR];
 #pragma unroll
             for (int w = 0; w < WPR; ++w) acc[w] = 0;
 #pragma unroll 1
-            for (int k = kmax - 1; k >= 1; --k) {
-                uint32_t *p = plane_ptr(k);
+            for (int k = kmax - 1; k > NPSL; --k) {
+                uint32_t *p = gl_plane(k);
                 uint32_t v[WPR];
                 Row<WPR>::ld(p, v);
 #pragma unroll
                 for (int w = 0; w < WPR; ++w) { acc[w] ^= v[w]; v[w] = acc[w]; }
                 Row<WPR>::st(p, v);
             }
-            uint32_t V[WPR];
-            Row<WPR>::ld(&pf[row * WPR], V);
+#pragma unroll 1
+            for (int k = min(kmax - 1, NPSL); k >= 1; --k) {
+                uint32_t *p = pls + (k - 1) * PLANE_WORDS;
+                uint32_t v[WPR];
+                sm_ld(p, P, row, v);
 #pragma unroll
-            for (int w = 0; w < WPR; ++w) { B0[w] = kmax > 0 ? (acc[w] ^ G0[w]) : 0u; V[w] &= ~A[w]; }
-            Row<WPR>::st(&pv[row * WPR], V);
+                for (int w = 0; w < WPR; ++w) { acc[w] ^= v[w]; v[w] = acc[w]; }
+                sm_st(p, P, row, v);
+            }
+            uint32_t V[WPR], FRr[WPR];
+            Row<WPR>::ld(free_g, FRr);
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) { B0[w] = kmax > 0 ? (acc[w] ^ G0[w]) : 0u; V[w] = FRr[w] & ~A[w]; }
+            sm_st(pv, P, row, V);     // the frontier buffers are dead: every thread left the loop through the barrier
+            sm_st(pf, P, row, FRr);
         }
         __syncthreads();
 
@@ -225,7 +245,7 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
             const uint32_t *p1 = pls, *p2 = pls + PLANE_WORDS;       // binary cost bits 1 and 2
             const bool has1 = kmax > 1, has2 = kmax > 2;
             auto ldw = [&](const uint32_t *pl_, bool on, int r, int w) -> uint32_t {
-                return (on && r >= 0 && r < P && w >= 0 && w < WPR) ? pl_[r * WPR + w] : 0u;
+                return (on && r >= 0 && r < P && w >= 0 && w < WPR) ? pl_[((w >> 2) * P + r) * 4 + (w & 3)] : 0u;
             };
             // value of the cell at column+1 / column-1 aligned to word w of row r
             auto hiw = [&](const uint32_t *pl_, bool on, int r, int w) { return (ldw(pl_, on, r, w) >> 1) | (ldw(pl_, on, r, w + 1) << 31); };
@@ -281,13 +301,13 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
                 uint32_t bw[NPMAX];
 #pragma unroll
                 for (int k = 0; k < NPMAX; ++k) bw[k] = 0;
-                const uint32_t vis = pv[row * WPR + w];
+                const uint32_t vis = pv[((w >> 2) * P + row) * 4 + (w & 3)];
 #pragma unroll
                 for (int u = 0; u < WPR; ++u)
                     if (u == w) bw[0] = B0[u];
 #pragma unroll
                 for (int k = 1; k < NPMAX; ++k)
-                    if (k < kmax) bw[k] = plane_ptr(k)[w];
+                    if (k < kmax) bw[k] = k <= NPSL ? pls[(k - 1) * PLANE_WORDS + ((w >> 2) * P + row) * 4 + (w & 3)] : gl_plane(k)[w];
                 uint32_t lo8[8], hi8[8], top8[8];   // cost bits 0-7 / 8-15 / 16-17 of the 32 cells, 4 cells per word
                 {
                     uint32_t tl[4], th[4];
@@ -336,7 +356,7 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
                 }
             }
         }
-        __syncthreads();   // the planes and `bnd` are reused by the next grid
+        __syncthreads();   // the planes are reused by the next grid
     }
 
     if (a.ticket && tid == 0) {
@@ -353,7 +373,7 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
 int large_wpr(int G) { return G <= 256 ? 8 : 16; }
 size_t large_smem_bytes(int G) {
     const int wpr = large_wpr(G);
-    return static_cast<size_t>(NSM) * 32 * wpr * wpr * sizeof(uint32_t);
+    return (static_cast<size_t>(NPSL) * 32 * wpr * wpr + 2 * static_cast<size_t>(32 * wpr + 2) * wpr) * sizeof(uint32_t);
 }
 
 }  // namespace
@@ -362,7 +382,7 @@ bool flow_field_large_supported(int G) { return G > 128 && G <= 512 && (G % 32) 
 
 size_t flow_field_large_scratch_words(int G) {
     const int wpr = large_wpr(G);
-    return static_cast<size_t>(NPGL) * 32 * wpr * wpr;
+    return static_cast<size_t>(NPGL + 1) * 32 * wpr * wpr;    // Gray planes NPSL+1.. and the free mask
 }
 
 int flow_field_large_max_grid(int G) {
