@@ -519,7 +519,6 @@ int ffmp_op_flow_field(int32_t device, int32_t n, int32_t G, const uint8_t *occ_
                        int32_t *cost_dev, uint8_t *flow_dev, void *workspace_dev, void *stream) {
     if (n < 0 || !occ_dev || !goal_cells_dev || !flow_dev || !workspace_dev) return fail(FFMP_ERR_ARG, "bad argument");
     if (!ffmp::flow_field_supported(G)) return fail(FFMP_ERR_ARG, "G must be a multiple of 4 in [16,128] or a multiple of 32 in (128,512]");
-    if (G > 128 && !cost_dev) return fail(FFMP_ERR_ARG, "the large-map kernel needs the cost plane (cost_dev != NULL)");
     if (reinterpret_cast<uintptr_t>(occ_dev) % 16 || reinterpret_cast<uintptr_t>(flow_dev) % 16 ||
         reinterpret_cast<uintptr_t>(cost_dev) % 16)
         return fail(FFMP_ERR_ARG, "occ / cost / flow must be 16-byte aligned");

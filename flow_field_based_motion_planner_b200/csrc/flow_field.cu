@@ -21,6 +21,7 @@
 //     transposes; the cost planes become bytes the same way, are staged (XOR-swizzled) in the plane storage they
 //     came from, and are widened to int32 with fully coalesced 16-byte stores.
 // Algorithmic HBM bytes: 6 B/cell (1 occ read + 4 cost write + 1 flow write).
+#include <cstdlib>
 #include <type_traits>
 
 #include "flow_bits.cuh"
@@ -545,12 +546,22 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
 bool flow_field_large_supported(int G);
 int flow_field_large_max_grid(int G);
 size_t flow_field_large_scratch_words(int G);
+bool flow_field_rows_usable(int G);
+
+// FFMP_FLOW_ROWS=1: grids up to 128 with G % 32 == 0 also use the CTA-per-grid row kernel of flow_field_large.cu (lower
+// latency per grid and a smaller footprint for the env's background regeneration, lower batch throughput; measured in
+// profiles/r01d_rows_small.txt).  Scratch sizes cover both kernels, so the switch may change between calls.
+static bool rows_for_small() {
+    const char *e = std::getenv("FFMP_FLOW_ROWS");
+    return e && std::atoi(e) != 0;
+}
 cudaError_t launch_flow_field_large(const FlowArgs &a, int grid, cudaStream_t st);
 
 bool flow_field_supported(int G) { return (G >= 16 && G <= 128 && (G % 4) == 0) || flow_field_large_supported(G); }
 
 size_t flow_field_scratch_words(int G) {
     if (G > 128) return flow_field_large_scratch_words(G);
+    if (flow_field_rows_usable(G)) return flow_field_large_scratch_words(G);     // >= the warp kernel's need
     // planes NPS..15 of the padded grid ((G+31)/32*32)^2 live in the per-CTA scratch (L2 resident)
     const int wpr = (G + 31) / 32;
     return static_cast<size_t>(NPG) * 32 * wpr * wpr;
@@ -567,7 +578,7 @@ int flow_field_max_grid(int G) {
 
 cudaError_t launch_flow_field(const FlowArgs &a_in, int grid, cudaStream_t st) {
     if (grid <= 0) return cudaSuccess;
-    if (a_in.G > 128) return launch_flow_field_large(a_in, grid, st);
+    if (a_in.G > 128 || (flow_field_rows_usable(a_in.G) && rows_for_small())) return launch_flow_field_large(a_in, grid, st);
     FlowArgs a = a_in;
     a.neg1 = 0xFFFFFFFFu;
     a.one = 1u;

@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
 
         // ---- 5. integration field: bit-planes -> int32 (INF for cells not reached) -----------------------
         // One mask word is one 128-byte line of cost: the thread writes it with eight 16-byte stores.
-        if (row < G) {
+        if (row < G && a.cost) {
             int32_t *cost = a.cost + plane * cells + static_cast<size_t>(row) * G;
 #pragma unroll 1
             for (int w = 0; w < WPR; ++w) {
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
     }
 }
 
-int large_wpr(int G) { return G <= 256 ? 8 : 16; }
+int large_wpr(int G) { return G <= 128 ? 4 : G <= 256 ? 8 : 16; }
 size_t large_smem_bytes(int G) {
     const int wpr = large_wpr(G);
     return (static_cast<size_t>(NPSL) * 32 * wpr * wpr + 2 * static_cast<size_t>(32 * wpr + 2) * wpr) * sizeof(uint32_t);
@@ -379,6 +379,7 @@ size_t large_smem_bytes(int G) {
 }  // namespace
 
 bool flow_field_large_supported(int G) { return G > 128 && G <= 512 && (G % 32) == 0; }
+bool flow_field_rows_usable(int G) { return G >= 32 && G <= 512 && (G % 32) == 0; }
 
 size_t flow_field_large_scratch_words(int G) {
     const int wpr = large_wpr(G);
@@ -387,14 +388,14 @@ size_t flow_field_large_scratch_words(int G) {
 
 int flow_field_large_max_grid(int G) {
     if (large_wpr(G) == 16) return 148;                       // 512 threads, 160 KB of planes: one CTA per SM
-    int per_sm = static_cast<int>((227 * 1024) / (large_smem_bytes(G) + 8 * 1024));
-    if (per_sm > 4) per_sm = 4;
+    int per_sm = static_cast<int>((227 * 1024) / (large_smem_bytes(G) + 2 * 1024));
+    const int reg_limit = large_wpr(G) == 8 ? 2 : 5;          // ~96 registers x 256 / 128 threads
+    if (per_sm > reg_limit) per_sm = reg_limit;
     return 148 * per_sm;
 }
 
 cudaError_t launch_flow_field_large(const FlowArgs &a_in, int grid, cudaStream_t st) {
     if (grid <= 0) return cudaSuccess;
-    if (!a_in.cost) return cudaErrorInvalidValue;   // the large-map kernel always writes the integration field
     FlowArgs a = a_in;
     a.neg1 = 0xFFFFFFFFu;
     a.one = 1u;
@@ -405,12 +406,17 @@ cudaError_t launch_flow_field_large(const FlowArgs &a_in, int grid, cudaStream_t
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(flow_field_rows_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(flow_field_rows_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(flow_field_rows_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(flow_field_rows_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(flow_field_rows_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024);
         if (ce != cudaSuccess) return ce;
         configured = true;
     }
     if (large_wpr(a.G) == 16) {
         if (a.generate) flow_field_rows_kernel<16, true><<<grid, 512, smem, st>>>(a);
         else flow_field_rows_kernel<16, false><<<grid, 512, smem, st>>>(a);
+    } else if (large_wpr(a.G) == 4) {
+        if (a.generate) flow_field_rows_kernel<4, true><<<grid, 128, smem, st>>>(a);
+        else flow_field_rows_kernel<4, false><<<grid, 128, smem, st>>>(a);
     } else {
         if (a.generate) flow_field_rows_kernel<8, true><<<grid, 256, smem, st>>>(a);
         else flow_field_rows_kernel<8, false><<<grid, 256, smem, st>>>(a);

@@ -48,7 +48,7 @@ def flow_field(occ, goal_cells, want_cost=True):
     occ = occ.contiguous()
     n, G = occ.shape[0], occ.shape[1]
     goals = goal_cells.to(device=occ.device, dtype=torch.int32).contiguous()
-    need_cost = want_cost or G > 128          # the large-map kernel computes directions from the cost plane
+    need_cost = want_cost
     cost = torch.empty((n, G, G), dtype=torch.int32, device=occ.device) if need_cost else None
     flow = torch.empty((n, G, G), dtype=torch.uint8, device=occ.device)
     if n == 0:

@@ -371,3 +371,41 @@ def test_env_collision_equals_reference_is_collision_on_crop(ffmp, cuda_device):
             checked += 1
     assert checked == 60 * N
     env.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# kernel variants behind environment switches (read by the library at create / launch time)
+# ---------------------------------------------------------------------------------------------------
+def test_rollout_pipe_kernel_variant(ffmp, monkeypatch):
+    """FFMP_TICK_PIPE=1: the persistent producer/consumer tick kernel.  4096 envs put 14 envs on every CTA, i.e. three
+    rounds through the 6-slot window ring (the empty-barrier protocol), 16 steps cross a frame-ring wrap."""
+    monkeypatch.setenv("FFMP_TICK_PIPE", "1")
+    rollout_parity(ffmp, 4096, 16, seed=5, grid=128, window=100, check_every=4)
+    rollout_parity(ffmp, 40, 300, seed=6, grid=64, window=32, max_steps=15, check_every=50)
+
+
+@pytest.mark.parametrize("G", [32, 64, 128])
+def test_flow_field_rows_kernel_on_small_grids(ffmp, cuda_device, G, monkeypatch):
+    """FFMP_FLOW_ROWS=1: the CTA-per-grid / thread-per-row kernel of the large-map path, on grids the warp kernel normally
+    takes; with and without the cost output."""
+    monkeypatch.setenv("FFMP_FLOW_ROWS", "1")
+    cases = special_cases(G)
+    cost, flow = run_flow(ffmp, cuda_device, [c[1] for c in cases], [c[2] for c in cases])
+    for k, (name, occ, goal) in enumerate(cases):
+        ec, ed, ef = oracle.flow_field(occ, goal[0], goal[1])
+        assert np.array_equal(cost[k], ec), (G, name, "cost", int((cost[k] != ec).sum()))
+        assert np.array_equal(flow[k], ef), (G, name, "flow", int((flow[k] != ef).sum()))
+    _, flow2 = run_flow(ffmp, cuda_device, [c[1] for c in cases], [c[2] for c in cases], want_cost=False)
+    assert np.array_equal(flow2, flow)
+
+
+def test_rollout_rows_kernel_regeneration(ffmp, monkeypatch):
+    """FFMP_FLOW_ROWS=1 inside the env: reset and background regeneration through the row kernel."""
+    monkeypatch.setenv("FFMP_FLOW_ROWS", "1")
+    rollout_parity(ffmp, 48, 300, seed=11, grid=128, window=100, max_steps=20, check_every=50)
+
+
+def test_flow_field_large_without_cost(ffmp, cuda_device):
+    occ, _, _, cells = oracle.scenario(5, 0, 0, 256, p_occ=0.2, block_shift=2)
+    _, flow = run_flow(ffmp, cuda_device, [occ], [(cells[2], cells[3])], want_cost=False)
+    assert np.array_equal(flow[0], oracle.flow_field(occ, cells[2], cells[3])[2])
