@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--grid", type=int, default=128)
     ap.add_argument("--window", type=int, default=100)
     ap.add_argument("--ring", type=int, default=8)
-    ap.add_argument("--slots", type=int, default=6)
+    ap.add_argument("--slots", type=int, default=8)
     ap.add_argument("--goal-mode", type=int, default=0)
     ap.add_argument("--p-occ", type=float, default=0.10)
     ap.add_argument("--seed", type=int, default=1234)

@@ -142,24 +142,35 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
             // ---- 2. bytes -> free-cell bit mask: one byte per lane and one warp vote per 32 cells; the vote lands in
             //      the register of the lane that owns the row (static register indices, rolled over the owner lane) ----
             {
-                const uint8_t *stage = reinterpret_cast<const uint8_t *>(pl);
+                const uint8_t *stage = reinterpret_cast<const uint8_t *>(pl) + lane;
+                if (G == 32 * WPR) {
+                    // exact fit: word (R, w) is the 32 bytes at (R * WPR + w) * 32; per word LDS.U8, compare, vote, select
 #pragma unroll 1
-                for (int o = 0; o < 32; ++o) {
-                    const bool mine = lane == o;
+                    for (int o = 0; o < 32; ++o) {
+                        const bool mine = lane == o;
+                        const uint8_t *src = stage + o * (RPL * WPR * 32);
 #pragma unroll
-                    for (int r = 0; r < RPL; ++r) {
-                        const int R = o * RPL + r;
+                        for (int r = 0; r < RPL; ++r)
 #pragma unroll
-                        for (int w = 0; w < WPR; ++w) {
-                            bool fr;
-                            if (G == 32 * WPR) {
-                                fr = stage[(R * WPR + w) * 32 + lane] == 0;
-                            } else {
-                                const int col = 32 * w + lane;
-                                fr = (R < G && col < G) ? stage[R * G + col] == 0 : false;
+                            for (int w = 0; w < WPR; ++w) {
+                                const uint32_t bits = __ballot_sync(FULL, src[(r * WPR + w) * 32] == 0);
+                                if (mine) A[r][w] = bits;
                             }
-                            const uint32_t bits = __ballot_sync(FULL, fr);
-                            if (mine) A[r][w] = bits;
+                    }
+                } else {
+#pragma unroll 1
+                    for (int o = 0; o < 32; ++o) {
+                        const bool mine = lane == o;
+#pragma unroll
+                        for (int r = 0; r < RPL; ++r) {
+                            const int R = o * RPL + r;
+#pragma unroll
+                            for (int w = 0; w < WPR; ++w) {
+                                const int col = 32 * w + lane;
+                                const bool fr = (R < G && col < G) ? stage[R * G + 32 * w] == 0 : false;
+                                const uint32_t bits = __ballot_sync(FULL, fr);
+                                if (mine) A[r][w] = bits;
+                            }
                         }
                     }
                 }

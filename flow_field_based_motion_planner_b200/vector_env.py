@@ -215,17 +215,18 @@ class FFMPVectorEnv:
                 pin = dict(pin_memory=True)
                 r, g, v = torch.empty(N, dtype=torch.float32, **pin), torch.empty((N, 2), dtype=torch.float32, **pin), torch.empty((N, 2), dtype=torch.float32, **pin)
                 dn, fl = torch.empty(N, dtype=torch.uint8, **pin), torch.empty(N, dtype=torch.uint8, **pin)
-            self._host = {"reward": r, "rel_goal": g, "velocity": v, "done": dn, "flags": fl}
+            self._host = {"reward": r, "rel_goal": g, "velocity": v, "done": dn, "flags": fl, "done_bool": dn.view(torch.bool),
+                          "info": {"flags": fl}}
             self._host_ptrs = tuple(C.c_void_p(self._host[k].data_ptr()) for k in ("reward", "done", "flags", "rel_goal", "velocity"))
         hst = self._host
         a = actions_host
         assert a.dtype == torch.int64 and a.device.type == "cpu" and a.numel() == N and a.is_contiguous()
-        with torch.cuda.device(self.device):
-            native.check(self._L.ffmp_step_host(self._h, C.c_void_p(a.data_ptr()), *self._host_ptrs, self._stream()),
-                         "ffmp_step_host")
-        obs = self._obs()
-        obs = {"local_map": obs["local_map"], "relative_goal": hst["rel_goal"], "velocity": hst["velocity"]}
-        return obs, hst["reward"], hst["done"].view(torch.bool), {"flags": hst["flags"]}
+        # the library switches to its own device (DeviceGuard) and synchronises the stream: no torch device context here
+        rc = self._L.ffmp_step_host(self._h, C.c_void_p(a.data_ptr()), *self._host_ptrs, self._stream())
+        if rc:
+            native.check(rc, "ffmp_step_host")
+        obs = {"local_map": self._obs()["local_map"], "relative_goal": hst["rel_goal"], "velocity": hst["velocity"]}
+        return obs, hst["reward"], hst["done_bool"], hst["info"]
 
     @property
     def h2d_bytes_per_step(self):
