@@ -120,6 +120,7 @@ struct ffmp_handle {
     bool use_tma = false;
     bool fused = true;              // one kernel per tick (env FFMP_STEP_FUSED=0 selects dynamics + observe kernels)
     bool pipe = false;              // FFMP_TICK_PIPE=1: steps use the experimental tick_pipe_kernel instead of tick_tma_kernel
+    bool spec = false;              // FFMP_TICK_SPEC=1: steps use the experimental tick_spec_kernel (speculative drain)
     // optional per-kernel timing (ffmp_timing): events [before tick, after tick] on the caller's stream and
     // [before regeneration, after regeneration] on the side stream of the tick
     static constexpr int TIMING_RING = 256;
@@ -194,7 +195,7 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
     const bool one_kernel = h->use_tma && h->fused;
     cudaEvent_t *tev = (h->timing && h->timing_n < ffmp_handle::TIMING_RING) ? h->tev[h->timing_n++] : nullptr;
     if (tev) CK(cudaEventRecord(tev[0], st));
-    CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st, nullptr, h->fused, h->pipe));
+    CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st, nullptr, h->fused, h->pipe, h->spec));
     if (tev) CK(cudaEventRecord(tev[1], st));
     h->launches += one_kernel ? 1 : 2;
     CK(cudaEventRecord(h->ev_step[l], st));
@@ -247,6 +248,7 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
     h->cfg = *cfg;
     if (const char *f = std::getenv("FFMP_STEP_FUSED")) h->fused = std::atoi(f) != 0;
     if (const char *f = std::getenv("FFMP_TICK_PIPE")) h->pipe = std::atoi(f) != 0;
+    if (const char *f = std::getenv("FFMP_TICK_SPEC")) h->spec = std::atoi(f) != 0;
     h->ws = workspace_layout(cfg);
     h->nlist = cfg->slots - 1;
     std::memset(&h->b, 0, sizeof(h->b));

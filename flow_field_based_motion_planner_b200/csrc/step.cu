@@ -317,13 +317,14 @@ __device__ __forceinline__ void tma_window(uint32_t dst, const CUtensorMap *tm, 
 template <bool TWO>
 __device__ __forceinline__ void drain_tile(const uint32_t *__restrict__ tile32, int tile_wpr, int G, int W, int wpr,
                                            int i0, int mis, int row0, int stride, int wl, uint32_t ormask,
-                                           uint32_t *__restrict__ dst, uint32_t *__restrict__ dst2) {
+                                           uint32_t *__restrict__ dst, uint32_t *__restrict__ dst2, int row_end = -1) {
     constexpr int U = 5;
+    const int RE = row_end < 0 ? W : row_end;                 // this call covers rows [row0, RE) of the frame
     const int sstep = stride * tile_wpr, dstep = stride * wpr;
     const int shift = 8 * (mis & 3);
-    const int r_in = max(-i0, 0), r_out = min(G - i0, W);     // in-grid rows are [r_in, r_out)
+    const int r_in = max(-i0, 0), r_out = min(G - i0, RE);     // in-grid rows are [r_in, r_out)
     int row = row0, s = row0 * tile_wpr + (mis >> 2) + wl, d = row0 * wpr + wl;
-    for (; row < min(r_in, W); row += stride, s += sstep, d += dstep) {
+    for (; row < min(r_in, RE); row += stride, s += sstep, d += dstep) {
         __stcs(dst + d, 0xFFFFFFFFu);
         if (TWO) __stcs(dst2 + d, 0xFFFFFFFFu);
     }
@@ -343,7 +344,7 @@ __device__ __forceinline__ void drain_tile(const uint32_t *__restrict__ tile32, 
         __stcs(dst + d, v);
         if (TWO) __stcs(dst2 + d, v);
     }
-    for (; row < W; row += stride, d += dstep) {
+    for (; row < RE; row += stride, d += dstep) {
         __stcs(dst + d, 0xFFFFFFFFu);
         if (TWO) __stcs(dst2 + d, 0xFFFFFFFFu);
     }
@@ -702,6 +703,199 @@ __global__ void __launch_bounds__(128) tick_tma_kernel(const __grid_constant__ C
     }
 }
 
+// ---- tick_spec_kernel: tick_tma_kernel with a SPECULATIVE drain (mode 0 only) ----------------------------------
+// The timeline of tick_tma_kernel (profiles/r01b_tick_trace.txt) serialises, after the window has landed, ~1 us of scalar
+// work in warp 0 (footprint test, reward, done, ten global stores) before the four warps start to stream the frame.  Here
+// warp 0 publishes the crop coordinates right after the kinematics; warps 1-3 wait for the window themselves and drain it
+// at once, speculating that the episode continues, while warp 0 does the scalar work and then drains a smaller share.
+// Only when the episode ended (or the ring wraps with a moved robot) a second window is fetched after a barrier and the
+// frame(s) are rewritten.
+struct SpecShared {
+    int ci, cj, pi, pj;        // new / previous robot cell of the speculative frame
+    unsigned int plane;
+    int redo;                  // 1: the episode ended, (ci, cj, plane) now name the first window of the next scenario
+};
+
+__global__ void __launch_bounds__(128, 12) tick_spec_kernel(const __grid_constant__ CUtensorMap tmap, StepArgs a) {
+    extern __shared__ __align__(128) uint8_t tile[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ SpecShared sh;
+    const int e = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int G = a.G, W = a.W;
+    const int wpr = W >> 2;
+    const int tile_w = (W + 15 + 15) & ~15;
+    const int tile_wpr = tile_w >> 2;
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&mbar));
+    const uint32_t tile_s = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
+    const uint32_t bytes = static_cast<uint32_t>(tile_w * W);
+    const int half = W >> 1;
+    const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
+    uint32_t *f_new = reinterpret_cast<uint32_t *>(a.frames + (static_cast<size_t>(e) * a.K + a.slot_new) * W * W);
+    uint32_t *f_old = f_new - (W * W >> 2);
+    // rows [0, split) are drained by warps 1-3 (interleaved), rows [split, W) by warp 0 once its scalar work is done
+    const int split = W - (W >> 3);
+    int rpi = 1, sub = 0, wl = lane;
+    if (wpr <= 32) { rpi = 32 / wpr; sub = lane / wpr; wl = lane - sub * wpr; }
+    auto colmask = [&](int jbase, int w) {
+        uint32_t om = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (static_cast<unsigned>(jbase + 4 * w + c) >= static_cast<unsigned>(G)) om |= 0xFFu << (8 * c);
+        return om;
+    };
+    // this warp's share of one frame out of the staged tile
+    auto drain_share = [&](int ci_, int cj_, bool both, uint32_t *dst, uint32_t *dst2) {
+        const int i0 = ci_ - half, j0 = cj_ - half;
+        const int r0 = warp == 0 ? split : (warp - 1) * rpi, r1 = warp == 0 ? W : split, st = warp == 0 ? rpi : 3 * rpi;
+        if (wpr <= 32) {
+            if (sub < rpi) {
+                const uint32_t om = colmask(j0, wl);
+                if (both) drain_tile<true>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, r0 + sub, st, wl, om, dst, dst2, r1);
+                else drain_tile<false>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, r0 + sub, st, wl, om, dst, nullptr, r1);
+            }
+        } else {
+            for (int w2 = lane; w2 < wpr; w2 += 32) {
+                const uint32_t om = colmask(j0, w2);
+                const int rr0 = warp == 0 ? split : warp - 1, rst = warp == 0 ? 1 : 3;
+                if (both) drain_tile<true>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, rr0, rst, w2, om, dst, dst2, r1);
+                else drain_tile<false>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, rr0, rst, w2, om, dst, nullptr, r1);
+            }
+        }
+    };
+    const bool older = a.write_older != 0;     // ring wrap: every env also rewrites the older frame
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        uint32_t *st = a.state + static_cast<size_t>(e) * ST_WORDS;
+        const uint4 s0 = *reinterpret_cast<const uint4 *>(st);        // x y yaw gx
+        const uint4 s1 = *reinterpret_cast<const uint4 *>(st + 4);    // gy d_first return steps
+        const float x = __uint_as_float(s0.x), y = __uint_as_float(s0.y), yaw = __uint_as_float(s0.z);
+        const float gx = __uint_as_float(s0.w), gy = __uint_as_float(s1.x);
+        const float d_first = __uint_as_float(s1.y);
+        float ep_return = __uint_as_float(s1.z);
+        int steps = static_cast<int>(s1.w);
+        uint32_t episode = st[ST_EPISODE];
+        long long act = a.actions[e];
+        if (act < 0 || act >= 28) {
+            act = 3;
+            if (lane == 0) atomicOr(a.error_word, 1u);
+        }
+        float v, w, s, c;
+        action_lookup(static_cast<int>(act), v, w);
+        sincos_spec(yaw, s, c);
+        const float nx = fadd(x, fmul(fmul(v, c), a.dt));
+        const float ny = fadd(y, fmul(fmul(v, s), a.dt));
+        const float nyaw = pi_to_pi(fadd(yaw, fmul(w, a.dt)));
+        const int ci = robot_cell(nx), cj = robot_cell(ny);
+        const int pi = robot_cell(x), pj = robot_cell(y);
+        const uint32_t plane = (episode % a.S) * static_cast<uint32_t>(a.N) + static_cast<uint32_t>(e);
+        if (lane == 0) {
+            sh.ci = ci; sh.cj = cj; sh.pi = pi; sh.pj = pj; sh.plane = plane; sh.redo = 0;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            tma_window(tile_s, &tmap, (cj - half) & ~15, ci - half, static_cast<int>(plane), bar);
+        }
+        __syncthreads();                                   // #1: the crop coordinates are public, the window is on its way
+        // math that does not depend on the map overlaps the copy
+        const float dx = fsub(gx, nx), dy = fsub(gy, ny);
+        const float d = dist_spec(dx, dy);
+        const float bearing = pi_to_pi(fsub(atan2_spec(dy, dx), nyaw));
+        const float vl = dist_spec(fsub(nx, x), fsub(ny, y));
+        const float va = pi_to_pi(fsub(nyaw, yaw));
+        const bool goal = d < 0.5f;
+        mbar_wait_parity(bar, 0);
+        bool hit = false;
+        if (lane < 21) {
+            int di, dj;
+            if (lane < 3) { di = -2; dj = lane - 1; }
+            else if (lane < 18) { di = (lane - 3) / 5 - 1; dj = (lane - 3) % 5 - 2; }
+            else { di = 2; dj = lane - 19; }
+            const int i = ci + di, j = cj + dj;
+            hit = static_cast<unsigned>(i) >= static_cast<unsigned>(G) || static_cast<unsigned>(j) >= static_cast<unsigned>(G);
+            if (!hit) hit = tile[(half + di) * tile_w + ((cj - half) & 15) + half + dj] == 255;
+        }
+        const bool col = __ballot_sync(FULL, hit) != 0;
+        const float r = fadd(fadd(goal ? 1.0f : fmul(0.05f, fsub(d_first, d)), col ? -1.0f : 0.0f), -0.05f);
+        steps += 1;
+        const bool trunc = steps == a.max_steps;
+        const bool done = col || goal || trunc;
+        ep_return = fadd(ep_return, r);
+        if (lane == 0) {
+            a.reward[e] = r;
+            a.done[e] = done ? 1 : 0;
+            a.flags[e] = static_cast<uint8_t>((col ? 1 : 0) | (goal ? 2 : 0) | (trunc ? 4 : 0));
+            *reinterpret_cast<float2 *>(a.term_rel_goal + 2 * e) = make_float2(d, bearing);
+            *reinterpret_cast<float2 *>(a.term_velocity + 2 * e) = make_float2(vl, va);
+        }
+        if (!done) {
+            if (lane == 0) {
+                st[ST_X] = __float_as_uint(nx); st[ST_Y] = __float_as_uint(ny); st[ST_YAW] = __float_as_uint(nyaw);
+                st[ST_RETURN] = __float_as_uint(ep_return);
+                st[ST_STEPS] = static_cast<uint32_t>(steps);
+                *reinterpret_cast<float2 *>(a.rel_goal + 2 * e) = make_float2(d, bearing);
+                *reinterpret_cast<float2 *>(a.velocity + 2 * e) = make_float2(vl, va);
+            }
+            drain_share(ci, cj, older && pi == ci && pj == cj, f_new, f_old);
+        } else {
+            // episode end: begin the next pre-generated scenario; its first window is fetched after barrier #2
+            episode += 1;
+            const uint32_t *rec = a.scen + (static_cast<size_t>(episode % a.S) * a.N + e) * SC_WORDS;
+            const uint4 r0 = *reinterpret_cast<const uint4 *>(rec);
+            const float sx = __uint_as_float(r0.x), sy = __uint_as_float(r0.y), syaw = __uint_as_float(r0.z);
+            const float ngx = __uint_as_float(r0.w), ngy = __uint_as_float(rec[SC_GY]);
+            const float ndx = fsub(ngx, sx), ndy = fsub(ngy, sy);
+            const float nd = dist_spec(ndx, ndy);
+            const float nbearing = pi_to_pi(fsub(atan2_spec(ndy, ndx), syaw));
+            if (lane == 0) {
+                a.fin_return[e] = ep_return;
+                a.fin_length[e] = steps;
+                const uint32_t idx = atomicAdd(a.regen_count, 1u);
+                a.regen_env[idx] = static_cast<uint32_t>(e);
+                a.regen_episode[idx] = episode + static_cast<uint32_t>(a.S) - 1u;
+                *reinterpret_cast<uint4 *>(st) = make_uint4(__float_as_uint(sx), __float_as_uint(sy), __float_as_uint(syaw), __float_as_uint(ngx));
+                *reinterpret_cast<uint4 *>(st + 4) = make_uint4(__float_as_uint(ngy), __float_as_uint(nd), __float_as_uint(0.0f), 0u);
+                st[ST_EPISODE] = episode;
+                *reinterpret_cast<float2 *>(a.rel_goal + 2 * e) = make_float2(nd, nbearing);
+                *reinterpret_cast<float2 *>(a.velocity + 2 * e) = make_float2(0.0f, 0.0f);
+                sh.ci = robot_cell(sx); sh.cj = robot_cell(sy);
+                sh.plane = (episode % a.S) * static_cast<uint32_t>(a.N) + static_cast<uint32_t>(e);
+                sh.redo = 1;
+            }
+        }
+    } else {
+        __syncthreads();                                   // #1
+        const int ci = sh.ci, cj = sh.cj, pi = sh.pi, pj = sh.pj;
+        mbar_wait_parity(bar, 0);
+        drain_share(ci, cj, older && pi == ci && pj == cj, f_new, f_old);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of `tile` precede a possible async overwrite
+    __syncthreads();                                       // #2: the verdict of warp 0 is public
+    const int redo = sh.redo;
+    const int ci = sh.ci, cj = sh.cj, pi = sh.pi, pj = sh.pj;
+    if (redo) {
+        // first observation of the new episode: both frames are the window at the start pose
+        if (tid == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            tma_window(tile_s, &tmap, (cj - half) & ~15, ci - half, static_cast<int>(sh.plane), bar);
+        }
+        mbar_wait_parity(bar, 1);
+        drain_share(ci, cj, true, f_new, f_old);
+    } else if (older && !(pi == ci && pj == cj)) {
+        // ring wrap of a continuing env that moved: the older frame is the window at the previous pose
+        if (tid == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            tma_window(tile_s, &tmap, (pj - half) & ~15, pi - half, static_cast<int>(sh.plane), bar);
+        }
+        mbar_wait_parity(bar, 1);
+        drain_share(pi, pj, false, f_old, nullptr);
+    }
+}
+
 // ---- tick_pipe_kernel: the env step as a persistent producer / consumer pipeline ---------------------------------
 // The per-CTA timeline of tick_tma_kernel (profiles/r01b_tick_trace.txt) is a 4.5-5.5 us dependent chain (state load ->
 // kinematics -> window TMA -> footprint -> drain) with one window in flight per CTA, i.e. ~12 windows per SM: not enough
@@ -984,7 +1178,8 @@ __global__ void __launch_bounds__(128) rewarder_kernel(RewarderArgs a) {
 
 }  // namespace
 
-cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t st, cudaEvent_t between, bool fused, bool pipe) {
+cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t st, cudaEvent_t between, bool fused, bool pipe,
+                        bool spec) {
     if (a.N <= 0) return cudaSuccess;
     const size_t smem = tmap ? static_cast<size_t>((a.W + 30) & ~15) * a.W + 16 : 0;
     if (tmap) {
@@ -994,11 +1189,17 @@ cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t
             if (ce == cudaSuccess)
                 ce = cudaFuncSetAttribute(tick_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
             if (ce == cudaSuccess)
+                ce = cudaFuncSetAttribute(tick_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (ce == cudaSuccess)
                 ce = cudaFuncSetAttribute(observe_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
             if (ce != cudaSuccess) return ce;
             configured = smem;
         }
         if (fused && !between) {
+            if (a.mode == 0 && spec && !pipe && !a.trace) {
+                tick_spec_kernel<<<a.N, 128, smem, st>>>(*tmap, a);
+                return cudaGetLastError();
+            }
             if (a.mode == 0 && pipe) {
                 // persistent producer / consumer pipeline: two CTAs per SM, at most 32 envs per CTA
                 const size_t tile_stride = (smem - 16 + 127) & ~static_cast<size_t>(127);
