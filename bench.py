@@ -306,9 +306,10 @@ def run_ours(a):
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        v, dt = cpu_port_throughput(a, 64, 300, 10, 1)
+        # a bounded sample of the same workload, ~10 s of single-thread CPU work
+        v, dt = cpu_port_throughput(a, 256, 2400, 20, 1)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"64 envs x 300 steps of the same workload, single thread, {dt:.1f} s (C oracle port)"}
+               "sample": f"256 envs x 2400 steps of the same workload, single thread, {dt:.1f} s (C oracle port, gcc -O2)"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
