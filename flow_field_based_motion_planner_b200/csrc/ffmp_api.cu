@@ -477,6 +477,20 @@ int ffmp_obs_slot(const ffmp_handle *h, int32_t *newest_slot) {
     return FFMP_OK;
 }
 
+int ffmp_learner_input(ffmp_handle *h, void *out_dev, int32_t dtype, float scale, void *stream) {
+    if (!h || !out_dev) return fail(FFMP_ERR_ARG, "null argument");
+    if (!h->ready) return fail(FFMP_ERR_STATE, "ffmp_reset must be called before ffmp_learner_input");
+    if (dtype != 0 && dtype != 1) return fail(FFMP_ERR_ARG, "dtype must be 0 (float32) or 1 (bfloat16)");
+    if (reinterpret_cast<uintptr_t>(out_dev) % 16) return fail(FFMP_ERR_ARG, "out must be 16-byte aligned");
+    DeviceGuard guard(h->cfg.device);
+    ffmp::FeedArgs a{};
+    a.N = h->cfg.num_envs; a.K = h->cfg.ring; a.W = h->cfg.window; a.slot_new = h->p; a.bf16 = dtype;
+    a.scale = scale; a.frames = h->b.frames; a.out = out_dev;
+    CK(ffmp::launch_learner_input(a, static_cast<cudaStream_t>(stream)));
+    h->launches += 1;
+    return FFMP_OK;
+}
+
 int ffmp_join(ffmp_handle *h, void *stream) {
     if (!h) return fail(FFMP_ERR_ARG, "handle is null");
     DeviceGuard guard(h->cfg.device);

@@ -79,7 +79,15 @@ struct RewarderArgs {
     uint8_t *done, *flags;
 };
 
+struct FeedArgs {
+    int N, K, W, slot_new, bf16;
+    float scale;
+    const uint8_t *frames;      // [N][K][W][W]
+    void *out;                  // f32 or bf16 [N][2][W][W]
+};
+
 // launchers (each returns the cudaError_t of the launch)
+cudaError_t launch_learner_input(const FeedArgs &a, cudaStream_t st);
 cudaError_t launch_scenarios(const ScenarioArgs &a, int grid, cudaStream_t st);
 cudaError_t launch_flow_field(const FlowArgs &a, int grid, cudaStream_t st);
 // tmap: TMA descriptor of the flow planes [S*N][G][G] (box W x ceil16(W)) or null -> plain-load observe kernel

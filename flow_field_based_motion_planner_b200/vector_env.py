@@ -236,6 +236,20 @@ class FFMPVectorEnv:
     def d2h_bytes_per_step(self):
         return self.num_envs * (4 + 1 + 1 + 8 + 8)
 
+    def learner_input(self, dtype=torch.float32, scale=1.0, out=None):
+        """The current observation as the learner's input: float32 / bfloat16 [N, 2, W, W], oldest frame first (the
+        reference's `observe_m`, train.py:474-486, 539-545; scale=1.0 is its plain `.float()`)."""
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("dtype must be torch.float32 or torch.bfloat16")
+        N, W = self.num_envs, self.config.window
+        if out is None:
+            out = torch.empty((N, 2, W, W), dtype=dtype, device=self.device)
+        assert out.dtype == dtype and out.device == self.device and out.is_contiguous() and out.numel() == N * 2 * W * W
+        with torch.cuda.device(self.device):
+            native.check(self._L.ffmp_learner_input(self._h, C.c_void_p(out.data_ptr()), 0 if dtype == torch.float32 else 1,
+                                                    C.c_float(scale), self._stream()), "ffmp_learner_input")
+        return out
+
     def join(self):
         """Order the current stream after all queued background scenario regeneration."""
         with torch.cuda.device(self.device):

@@ -409,3 +409,17 @@ def test_flow_field_large_without_cost(ffmp, cuda_device):
     occ, _, _, cells = oracle.scenario(5, 0, 0, 256, p_occ=0.2, block_shift=2)
     _, flow = run_flow(ffmp, cuda_device, [occ], [(cells[2], cells[3])], want_cost=False)
     assert np.array_equal(flow[0], oracle.flow_field(occ, cells[2], cells[3])[2])
+
+
+def test_learner_input_matches_float_cast(ffmp, cuda_device):
+    """ffmp_learner_input == the reference's observe_m: cat of the last two frames, `.float()` (train.py:474-486, 539-545)."""
+    env = ffmp.FFMPVectorEnv(37, grid=64, window=32, ring=4, seed=2)
+    obs = env.reset()
+    rng = np.random.default_rng(2)
+    for t in range(9):      # crosses two ring wraps
+        obs, _, _, _ = env.step(torch.as_tensor(rng.integers(0, 28, 37), device=cuda_device))
+        want = obs["local_map"].float()
+        assert torch.equal(env.learner_input(), want)
+        assert torch.equal(env.learner_input(dtype=torch.bfloat16).float(), want)
+        assert torch.allclose(env.learner_input(scale=1.0 / 255.0), want / 255.0, rtol=0, atol=1e-7)
+    env.close()

@@ -71,6 +71,11 @@ def main():
     # the bench workload
     env = ffmp.FFMPVectorEnv(N, grid=G, window=W, ring=a.ring, slots=a.slots, seed=1234)
     env.reset()
+    for dt, nm, wb in ((torch.float32, "f32", 4), (torch.bfloat16, "bf16", 2)):
+        out = torch.empty((N, 2, W, W), dtype=dt, device=dev)
+        med, _ = timed(lambda: env.learner_input(dtype=dt, out=out))
+        res[f"learner_input_{nm}_us"] = med * 1e3
+        res[f"learner_input_{nm}_frac"] = N * 2 * W * W * (1 + wb) / (med * 1e-3) / 6549.8e9
     acts = torch.randint(0, 28, (250, N), device=dev)
     for _ in range(2):
         env.rollout(acts)
