@@ -225,7 +225,12 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
                     for (int w = 0; w < WPR; ++w) G1[r][w] ^= A[r][w];
             } else {
                 const int k = __ffs(L) - 1;
-                if (k < NPS) {
+                if (KSEL == 3 && k == 1) {
+#pragma unroll
+                    for (int r = 0; r < RPL; ++r)
+#pragma unroll
+                        for (int w = 0; w < WPR; ++w) G1[r][w] ^= A[r][w];
+                } else if (k < NPS) {
 #pragma unroll
                     for (int r = 0; r < RPL; ++r) {
                         uint32_t v[WPR];
@@ -268,16 +273,20 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
                 for (int w = 0; w < WPR; ++w) {
                     A[r][w] = sub_on_fma(A[r][w], Nw[r][w], neg1);
                     F[r][w] = Nw[r][w];
-                    if constexpr (KSEL == 2) any |= Nw[r][w];
+                    if constexpr (KSEL >= 2) any |= Nw[r][w];
                 }
             return any;
         };
+        // Two levels of code (odd level: Gray plane 0, static; even level: plane ctz(L) >= 1, dynamic) executed twice per
+        // convergence vote: half the instruction footprint of a four-level body (the loop showed 13 % no-instruction stalls).
         uint32_t L = 1;
         for (;; L += 4) {
-            level(Int<0>{}, L);
-            level(Int<1>{}, L + 1);
-            level(Int<0>{}, L + 2);
-            const uint32_t any = level(Int<2>{}, L + 3);
+            uint32_t any = 0;
+#pragma unroll 1
+            for (uint32_t h = 0; h < 4; h += 2) {
+                level(Int<0>{}, L + h);
+                any = level(Int<3>{}, L + h + 1);
+            }
             if (!__any_sync(FULL, any != 0)) break;     // an empty frontier stays empty: test every fourth level
         }
 #pragma unroll
