@@ -40,7 +40,7 @@ struct DeviceGuard {
 };
 
 constexpr int MAX_LISTS = 7;
-constexpr int REGEN_GRID = 148 * 4;   // CTAs of a background regeneration launch
+constexpr int REGEN_GRID = 148 * 2;   // CTAs of a background regeneration launch (grids are handed out dynamically)
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
