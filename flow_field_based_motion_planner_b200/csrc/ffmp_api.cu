@@ -39,7 +39,7 @@ struct DeviceGuard {
     }
 };
 
-constexpr int MAX_LISTS = 7;
+constexpr int MAX_LISTS = 15;
 constexpr int REGEN_GRID = 148 * 2;   // CTAs of a background regeneration launch (grids are handed out dynamically)
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -72,7 +72,7 @@ int check_cfg(const ffmp_cfg *c) {
     if (!ffmp::flow_field_supported(c->grid)) return fail(FFMP_ERR_ARG, "grid must be <= 128, or a multiple of 32 up to 512");
     if (c->window < 4 || c->window > 256 || (c->window % 4)) return fail(FFMP_ERR_ARG, "window must be a multiple of 4 in [4,256]");
     if (c->ring < 2 || c->ring > 1024) return fail(FFMP_ERR_ARG, "ring must be in [2,1024]");
-    if (c->slots < 2 || c->slots > MAX_LISTS + 1) return fail(FFMP_ERR_ARG, "slots must be in [2,8]");
+    if (c->slots < 2 || c->slots > MAX_LISTS + 1) return fail(FFMP_ERR_ARG, "slots must be in [2,16]");
     if (c->max_steps <= 0) return fail(FFMP_ERR_ARG, "max_steps must be > 0");
     if (c->goal_mode != 0 && c->goal_mode != 1) return fail(FFMP_ERR_ARG, "goal_mode must be 0 or 1");
     if (c->block_shift < 0 || c->block_shift > 8) return fail(FFMP_ERR_ARG, "block_shift must be in [0,8]");

@@ -39,7 +39,7 @@ class FFMPConfig:
     grid: int = 128                 # G
     window: int = MAP_GRID_NUM      # W (local map side)
     ring: int = 8                   # K observation frame slots (2 = contiguous [N,2,W,W])
-    slots: int = 6                  # S resident scenario slots per env (S-1 regenerations in flight)
+    slots: int = 8                  # S resident scenario slots per env (S-1 regenerations in flight; 2..16)
     max_steps: int = MAX_STEPS
     goal_mode: int = 0              # 0 re-sampled per episode, 1 static at (G-8, G-8)
     block_shift: int = 3

@@ -51,7 +51,7 @@ typedef struct ffmp_cfg {
     int32_t grid;          /* G: global grid side, G%4==0, 16..1024            (reference map: 100, ffmp.py:15) */
     int32_t window;        /* W: local map side, W%4==0, <= 256                (ffmp.py:15: 100) */
     int32_t ring;          /* K >= 2 observation frame slots per env (SPEC.md §8) */
-    int32_t slots;         /* S >= 2 resident scenario slots per env (pre-generated episodes) */
+    int32_t slots;         /* S in [2,16] resident scenario slots per env (pre-generated episodes) */
     int32_t max_steps;     /* truncation                                       (train.py:60: 200) */
     int32_t goal_mode;     /* 0 goal re-sampled every episode, 1 static goal at (G-8,G-8) */
     int32_t block_shift;   /* obstacle block = 2^block_shift cells */

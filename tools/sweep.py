@@ -64,7 +64,7 @@ def run_flow(tag, n, G, p_occ, bs, reps=3):
 
 which = sys.argv[1:] or ["slots", "configs", "flow"]
 if "slots" in which:
-    for S in (3, 4, 6, 8):
+    for S in (3, 4, 6, 8, 12, 16):
         run_env(f"bench workload, slots={S}", num_envs=4096, grid=128, window=100, slots=S, seed=1234)
 if "configs" in which:
     run_env("config2: 1024 x 64x64, W=64, static goal", num_envs=1024, grid=64, window=64, goal_mode=1, seed=1234)
