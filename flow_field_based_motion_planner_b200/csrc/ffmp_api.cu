@@ -1,8 +1,10 @@
 // ffmp_api.cu — the C-ABI of libffmp_b200.so (include/ffmp_b200.h): handle, buffer binding, stream /
 // event plumbing for the background scenario regeneration, and the stateless operators.
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <new>
 #include <string>
 
@@ -41,6 +43,12 @@ struct DeviceGuard {
 
 constexpr int MAX_LISTS = 15;
 constexpr int REGEN_GRID = 148 * 2;   // CTAs of a background regeneration launch (grids are handed out dynamically)
+
+double now_us() {
+    timespec ts;
+    clock_gettime(CLOCK_REALTIME, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -128,6 +136,18 @@ struct ffmp_handle {
     int timing_n = 0;
     cudaEvent_t tev[TIMING_RING][4];
     uint64_t launches = 0;          // kernels launched by this handle (ffmp_launch_count)
+    // host-buffer steps (ffmp_step_host*): completion word in mapped pinned memory, written by host_export_kernel
+    volatile uint32_t *flag_host = nullptr;
+    uint32_t *flag_dev = nullptr;
+    uint32_t flag_seq = 0;
+    int host_io = 2;                // FFMP_HOST_IO: 0 copy engines + stream sync, 1 mapped results, 2 mapped results + zero-copy actions
+    int wait_mode = 0;              // what ffmp_step_host_wait has to do: 0 nothing, 1 spin on the flag, 2 synchronise wait_stream
+    cudaStream_t wait_stream = nullptr;
+    // FFMP_HOST_IO_STATS=1: host / device timeline of the host-buffer steps, printed to stderr by ffmp_destroy
+    bool io_stats = false;
+    double t_entry = 0, t_launched = 0, t_queued = 0;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t acc_n = 0;
     unsigned long long *trace = nullptr;   // FFMP_TRACE=1: [N][8] tick-kernel timestamps (library-owned, diagnostics only)
 
     uint32_t *error_word() const { return reinterpret_cast<uint32_t *>(static_cast<char *>(b.workspace) + ws.error_word); }
@@ -174,7 +194,8 @@ ffmp::StepArgs step_args(const ffmp_handle *h) {
 }
 
 // One env-step-like call (mode 0 step, mode 1 masked reset) with the background regeneration queued.
-int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *mask, cudaStream_t st) {
+int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *mask, cudaStream_t st,
+             const ffmp::HostExportArgs *host_export = nullptr) {
     const int l = static_cast<int>(h->step_index % static_cast<uint64_t>(h->nlist));
     if (h->regen_pending[l]) {
         // the regeneration that last used list `l` (S-1 ticks ago) must be complete: it re-armed the
@@ -196,6 +217,12 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
     cudaEvent_t *tev = (h->timing && h->timing_n < ffmp_handle::TIMING_RING) ? h->tev[h->timing_n++] : nullptr;
     if (tev) CK(cudaEventRecord(tev[0], st));
     CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st, nullptr, h->fused, h->pipe, h->spec));
+    if (host_export) {
+        // directly behind the step kernel (nothing in between), so that the programmatic dependency pairs the two
+        CK(ffmp::launch_host_export(*host_export, st));
+        h->launches += 1;
+        if (h->io_stats) h->t_launched = now_us();
+    }
     if (tev) CK(cudaEventRecord(tev[1], st));
     h->launches += one_kernel ? 1 : 2;
     CK(cudaEventRecord(h->ev_step[l], st));
@@ -249,6 +276,8 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
     if (const char *f = std::getenv("FFMP_STEP_FUSED")) h->fused = std::atoi(f) != 0;
     if (const char *f = std::getenv("FFMP_TICK_PIPE")) h->pipe = std::atoi(f) != 0;
     if (const char *f = std::getenv("FFMP_TICK_SPEC")) h->spec = std::atoi(f) != 0;
+    if (const char *f = std::getenv("FFMP_HOST_IO")) h->host_io = std::atoi(f);
+    if (const char *f = std::getenv("FFMP_HOST_IO_STATS")) h->io_stats = std::atoi(f) != 0;
     h->ws = workspace_layout(cfg);
     h->nlist = cfg->slots - 1;
     std::memset(&h->b, 0, sizeof(h->b));
@@ -260,9 +289,19 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_step[i], cudaEventDisableTiming);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_regen[i], cudaEventDisableTiming);
     }
+    if (ce == cudaSuccess) {
+        void *fh = nullptr, *fd = nullptr;
+        ce = cudaHostAlloc(&fh, 64, cudaHostAllocMapped);
+        if (ce == cudaSuccess) {
+            std::memset(fh, 0, 64);
+            h->flag_host = static_cast<volatile uint32_t *>(fh);
+            ce = cudaHostGetDevicePointer(&fd, fh, 0);
+            h->flag_dev = static_cast<uint32_t *>(fd);
+        }
+    }
     if (ce != cudaSuccess) {
         ffmp_destroy(h);
-        return fail(FFMP_ERR_CUDA, "stream/event creation", ce);
+        return fail(FFMP_ERR_CUDA, "stream / event / flag creation", ce);
     }
     if (const char *t = std::getenv("FFMP_TRACE")) {
         if (std::atoi(t) != 0 && cudaMalloc(&h->trace, static_cast<size_t>(cfg->num_envs) * 8 * sizeof(unsigned long long)) != cudaSuccess) {
@@ -332,7 +371,15 @@ int ffmp_destroy(ffmp_handle *h) {
         if (h->ev_step[i]) cudaEventDestroy(h->ev_step[i]);
         if (h->ev_regen[i]) cudaEventDestroy(h->ev_regen[i]);
     }
+    if (h->io_stats && h->acc_n) {
+        const double n = static_cast<double>(h->acc_n);
+        std::fprintf(stderr, "[ffmp host io] steps %llu  us/step: submit step+export %.2f | all queued %.2f | results seen %.2f || "
+                             "export resident->written %.2f (waiting for the step grid %.2f, copy+fence %.2f)\n",
+                     static_cast<unsigned long long>(h->acc_n), h->acc[0] / n, h->acc[1] / n, h->acc[2] / n, h->acc[3] / n,
+                     h->acc[4] / n, h->acc[5] / n);
+    }
     if (h->trace) cudaFree(h->trace);
+    if (h->flag_host) cudaFreeHost(const_cast<uint32_t *>(h->flag_host));
     if (h->tev[0][0])
         for (int i = 0; i < ffmp_handle::TIMING_RING; ++i)
             for (int j = 0; j < 4; ++j) cudaEventDestroy(h->tev[i][j]);
@@ -391,17 +438,28 @@ int ffmp_rollout(ffmp_handle *h, const int64_t *actions_dev, int32_t T, void *st
     return FFMP_OK;
 }
 
-int ffmp_step_host(ffmp_handle *h, const int64_t *actions_host, float *reward_host, uint8_t *done_host,
-                   uint8_t *flags_host, float *rel_goal_host, float *velocity_host, void *stream) {
+// Device-visible alias of a host pointer, or null when the memory is not pinned / mapped (then the copy engines are used).
+static void *mapped_alias(const void *p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
+int ffmp_step_host_async(ffmp_handle *h, const int64_t *actions_host, float *reward_host, uint8_t *done_host,
+                         uint8_t *flags_host, float *rel_goal_host, float *velocity_host, void *stream) {
     if (!h || !actions_host) return fail(FFMP_ERR_ARG, "null argument");
     if (!h->ready) return fail(FFMP_ERR_STATE, "ffmp_reset must be called before ffmp_step_host");
+    if (h->wait_mode) return fail(FFMP_ERR_STATE, "ffmp_step_host_wait must be called before the next ffmp_step_host_async");
     DeviceGuard guard(h->cfg.device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t N = h->cfg.num_envs;
-    CK(cudaMemcpyAsync(h->actions(), actions_host, N * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    if (int rc = run_tick(h, 0, h->actions(), nullptr, st)) return rc;
+    if (h->io_stats) h->t_entry = now_us();
     // When the five device outputs are adjacent in memory in the order reward | rel_goal | velocity | done | flags
-    // (FFMPVectorEnv allocates them so) and the host destinations are too, ONE device-to-host copy moves them.
+    // (FFMPVectorEnv allocates them so) and the host destinations are too, they move as ONE 22 N-byte block.
     const ffmp_buffers &b = h->b;
     const char *d0 = reinterpret_cast<const char *>(b.reward);
     char *h0 = reinterpret_cast<char *>(reward_host);
@@ -413,7 +471,35 @@ int ffmp_step_host(ffmp_handle *h, const int64_t *actions_host, float *reward_ho
                              reinterpret_cast<char *>(velocity_host) == h0 + 12 * N &&
                              reinterpret_cast<char *>(done_host) == h0 + 20 * N &&
                              reinterpret_cast<char *>(flags_host) == h0 + 21 * N;
-    if (dev_packed && host_packed) {
+    const bool packed = dev_packed && host_packed;
+
+    // mapped path: the export kernel writes the caller's pinned block and the completion word; no copy engine, no sync
+    void *out_alias = nullptr;
+    if (h->host_io >= 1 && packed && (22 * N) % 4 == 0 && reinterpret_cast<uintptr_t>(d0) % 16 == 0 &&
+        reinterpret_cast<uintptr_t>(h0) % 16 == 0)
+        out_alias = mapped_alias(h0);
+    const int64_t *actions_dev = nullptr;
+    if (out_alias && h->host_io >= 2) actions_dev = static_cast<const int64_t *>(mapped_alias(actions_host));
+    if (!actions_dev) {
+        CK(cudaMemcpyAsync(h->actions(), actions_host, N * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        actions_dev = h->actions();
+    }
+    if (out_alias) {
+        ffmp::HostExportArgs ea{};
+        ea.src = d0; ea.dst = out_alias;
+        ea.n16 = static_cast<int>(22 * N / 16);
+        ea.tail_words = static_cast<int>((22 * N % 16) / 4);
+        ea.flag = h->flag_dev;
+        ea.value = ++h->flag_seq;
+        if (h->io_stats) ea.stamps = reinterpret_cast<unsigned long long *>(h->flag_dev + 2);
+        if (int rc = run_tick(h, 0, actions_dev, nullptr, st, &ea)) return rc;
+        h->wait_mode = 1;
+        h->wait_stream = st;
+        if (h->io_stats) h->t_queued = now_us();
+        return FFMP_OK;
+    }
+    if (int rc = run_tick(h, 0, actions_dev, nullptr, st)) return rc;
+    if (packed) {
         CK(cudaMemcpyAsync(h0, d0, 22 * N, cudaMemcpyDeviceToHost, st));
     } else {
         if (reward_host) CK(cudaMemcpyAsync(reward_host, b.reward, N * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -422,8 +508,60 @@ int ffmp_step_host(ffmp_handle *h, const int64_t *actions_host, float *reward_ho
         if (rel_goal_host) CK(cudaMemcpyAsync(rel_goal_host, b.rel_goal, N * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
         if (velocity_host) CK(cudaMemcpyAsync(velocity_host, b.velocity, N * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
-    CK(cudaStreamSynchronize(st));
+    h->wait_mode = 2;
+    h->wait_stream = st;
     return FFMP_OK;
+}
+
+int ffmp_step_host_wait(ffmp_handle *h) {
+    if (!h) return fail(FFMP_ERR_ARG, "handle is null");
+    const int mode = h->wait_mode;
+    h->wait_mode = 0;
+    if (mode == 0) return FFMP_OK;
+    if (mode == 2) {
+        DeviceGuard guard(h->cfg.device);
+        CK(cudaStreamSynchronize(h->wait_stream));
+        return FFMP_OK;
+    }
+    // spin on the mapped completion word; every 2^14 polls ask the stream whether it died or drained without publishing
+    const uint32_t want = h->flag_seq;
+    for (uint32_t spins = 1;; ++spins) {
+        if (*h->flag_host == want) break;
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+        if ((spins & 0x3FFF) == 0) {
+            DeviceGuard guard(h->cfg.device);
+            const cudaError_t q = cudaStreamQuery(h->wait_stream);
+            if (q == cudaSuccess) {
+                if (*h->flag_host == want) break;
+                return fail(FFMP_ERR_CUDA, "the step finished without publishing its completion word");
+            }
+            if (q != cudaErrorNotReady) return fail(FFMP_ERR_CUDA, "ffmp_step_host_wait", q);
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (h->io_stats) {
+        // device stamps are globaltimer ns; they are anchored to the host clock at the flag (seen ~1 us after it is written)
+        const double t_seen = now_us();
+        const volatile unsigned long long *g = reinterpret_cast<const volatile unsigned long long *>(h->flag_host + 2);
+        const double g0 = g[0] * 1e-3, g1 = g[1] * 1e-3, g2 = g[2] * 1e-3;
+        h->acc[0] += h->t_launched - h->t_entry;   // entry -> step kernel + export kernel submitted
+        h->acc[1] += h->t_queued - h->t_entry;     // entry -> all of the tick's plumbing submitted (spin starts)
+        h->acc[2] += t_seen - h->t_entry;          // entry -> results seen
+        h->acc[3] += g2 - g0;                      // export kernel resident -> block written
+        h->acc[4] += g1 - g0;                      // export kernel resident -> step grid complete
+        h->acc[5] += g2 - g1;                      // step grid complete -> block written
+        h->acc_n += 1;
+    }
+    return FFMP_OK;
+}
+
+int ffmp_step_host(ffmp_handle *h, const int64_t *actions_host, float *reward_host, uint8_t *done_host,
+                   uint8_t *flags_host, float *rel_goal_host, float *velocity_host, void *stream) {
+    if (int rc = ffmp_step_host_async(h, actions_host, reward_host, done_host, flags_host, rel_goal_host, velocity_host, stream))
+        return rc;
+    return ffmp_step_host_wait(h);
 }
 
 int ffmp_timing(ffmp_handle *h, int32_t enable, float *tick_ms, float *regen_ms, int32_t *ticks) {

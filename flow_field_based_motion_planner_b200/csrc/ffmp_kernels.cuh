@@ -86,7 +86,17 @@ struct FeedArgs {
     void *out;                  // f32 or bf16 [N][2][W][W]
 };
 
+struct HostExportArgs {
+    const void *src;            // dev: packed result block (reward | rel_goal | velocity | done | flags), 16-byte aligned
+    void *dst;                  // device-visible address of the caller's pinned host block, 16-byte aligned
+    int n16, tail_words;        // 16-byte words, then 0..3 trailing 32-bit words
+    uint32_t *flag;             // device-visible address of the library's mapped completion word
+    uint32_t value;             // sequence number published when the block has been written
+    unsigned long long *stamps; // optional (diagnostics): three globaltimer stamps in mapped memory, or null
+};
+
 // launchers (each returns the cudaError_t of the launch)
+cudaError_t launch_host_export(const HostExportArgs &a, cudaStream_t st);   // host_io.cu: programmatic dependent of the tick
 cudaError_t launch_learner_input(const FeedArgs &a, cudaStream_t st);
 cudaError_t launch_scenarios(const ScenarioArgs &a, int grid, cudaStream_t st);
 cudaError_t launch_flow_field(const FlowArgs &a, int grid, cudaStream_t st);

@@ -505,6 +505,9 @@ __global__ void __launch_bounds__(128) tick_tma_kernel(const __grid_constant__ C
     };
     stamp(0);
     stamp(1);
+    // a programmatic dependent of this launch (host_export_kernel, host_io.cu) may become resident once every CTA of the
+    // tick has started; it still waits for the whole grid (griddepcontrol.wait) before it reads the results
+    asm volatile("griddepcontrol.launch_dependents;");
 
     if (warp == 0) {
         if (lane == 0) {

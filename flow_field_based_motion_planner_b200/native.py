@@ -13,7 +13,7 @@ COST_INF = 0x7FFFFFFF
 
 EXPORTS = [
     "ffmp_last_error", "ffmp_abi_version", "ffmp_query_sizes", "ffmp_create", "ffmp_bind", "ffmp_destroy",
-    "ffmp_reset", "ffmp_step", "ffmp_rollout", "ffmp_step_host", "ffmp_obs_slot", "ffmp_join", "ffmp_error_word", "ffmp_timing", "ffmp_launch_count", "ffmp_debug_trace", "ffmp_learner_input",
+    "ffmp_reset", "ffmp_step", "ffmp_rollout", "ffmp_step_host", "ffmp_step_host_async", "ffmp_step_host_wait", "ffmp_obs_slot", "ffmp_join", "ffmp_error_word", "ffmp_timing", "ffmp_launch_count", "ffmp_debug_trace", "ffmp_learner_input",
     "ffmp_op_scenarios", "ffmp_op_flow_field_workspace", "ffmp_op_flow_field", "ffmp_op_rewarder", "ffmp_op_rewarder2", "ffmp_op_reward_calculator",
 ]
 
@@ -68,6 +68,8 @@ def lib() -> C.CDLL:
     L.ffmp_step.argtypes = [vp, vp, vp]
     L.ffmp_rollout.argtypes = [vp, vp, i32, vp]
     L.ffmp_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ffmp_step_host_async.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ffmp_step_host_wait.argtypes = [vp]
     L.ffmp_obs_slot.argtypes = [vp, C.POINTER(i32)]
     L.ffmp_join.argtypes = [vp, vp]
     L.ffmp_timing.argtypes = [vp, i32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(i32)]

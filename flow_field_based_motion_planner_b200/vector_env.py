@@ -203,9 +203,7 @@ class FFMPVectorEnv:
             native.check(self._L.ffmp_rollout(self._h, C.c_void_p(a.data_ptr()), int(a.shape[0]), self._stream()), "ffmp_rollout")
         return self._obs(), self.reward, self._done_bool, self._info()
 
-    def step_host(self, actions_host):
-        """Host-buffer step: actions int64[N] in (pinned) host memory -> (obs, reward, done, info) with reward,
-        done, flags, relative_goal and velocity returned as host tensors; local_map stays on the device."""
+    def _host_buffers(self):
         N = self.num_envs
         if self._host is None:
             if N % 2 == 0:
@@ -218,15 +216,38 @@ class FFMPVectorEnv:
             self._host = {"reward": r, "rel_goal": g, "velocity": v, "done": dn, "flags": fl, "done_bool": dn.view(torch.bool),
                           "info": {"flags": fl}}
             self._host_ptrs = tuple(C.c_void_p(self._host[k].data_ptr()) for k in ("reward", "done", "flags", "rel_goal", "velocity"))
-        hst = self._host
+        return self._host
+
+    def step_async(self, actions_host):
+        """gym.vector's step_async with host buffers: queue one step on actions int64[N] in (pinned) host memory and
+        return at once; the buffer must stay untouched until step_wait() returns."""
+        self._host_buffers()
         a = actions_host
-        assert a.dtype == torch.int64 and a.device.type == "cpu" and a.numel() == N and a.is_contiguous()
-        # the library switches to its own device (DeviceGuard) and synchronises the stream: no torch device context here
-        rc = self._L.ffmp_step_host(self._h, C.c_void_p(a.data_ptr()), *self._host_ptrs, self._stream())
+        assert a.dtype == torch.int64 and a.device.type == "cpu" and a.numel() == self.num_envs and a.is_contiguous()
+        # the library switches to its own device (DeviceGuard): no torch device context here
+        rc = self._L.ffmp_step_host_async(self._h, C.c_void_p(a.data_ptr()), *self._host_ptrs, self._stream())
         if rc:
-            native.check(rc, "ffmp_step_host")
-        obs = {"local_map": self._obs()["local_map"], "relative_goal": hst["rel_goal"], "velocity": hst["velocity"]}
+            native.check(rc, "ffmp_step_host_async")
+        self._pending_actions = a        # keeps the buffer alive while the kernel reads it in place
+
+    def step_wait(self):
+        """gym.vector's step_wait: block until the step queued by step_async has delivered -> (obs, reward, done, info)
+        with reward, done, flags, relative_goal and velocity as pinned host tensors; local_map stays on the device."""
+        local_map = self._obs()["local_map"]           # host bookkeeping done while the GPU works
+        rc = self._L.ffmp_step_host_wait(self._h)
+        if rc:
+            native.check(rc, "ffmp_step_host_wait")
+        self._pending_actions = None
+        hst = self._host
+        obs = {"local_map": local_map, "relative_goal": hst["rel_goal"], "velocity": hst["velocity"]}
         return obs, hst["reward"], hst["done_bool"], hst["info"]
+
+    def step_host(self, actions_host):
+        """Host-buffer step: actions int64[N] in (pinned) host memory -> (obs, reward, done, info) with reward,
+        done, flags, relative_goal and velocity returned as host tensors; local_map stays on the device.
+        With pinned buffers nothing goes through a copy engine or a stream synchronisation (include/ffmp_b200.h)."""
+        self.step_async(actions_host)
+        return self.step_wait()
 
     @property
     def h2d_bytes_per_step(self):

@@ -117,14 +117,24 @@ int ffmp_step(ffmp_handle *h, const int64_t *actions_dev, void *stream);
 /* T back-to-back steps with actions_dev = i64[T][N]; identical to T ffmp_step calls. */
 int ffmp_rollout(ffmp_handle *h, const int64_t *actions_dev, int32_t T, void *stream);
 
-/* Host-buffer step (the reference-facing call with HOST memory): copies actions_host (i64[N], ideally
- * pinned) to the device, steps, copies reward f32[N], done u8[N], flags u8[N], rel_goal f32[N][2] and
- * velocity f32[N][2] back (any out pointer may be NULL) and synchronises `stream`.  The local_map
- * observation stays on the device.  If the five bound device outputs are adjacent in memory in the order
- * reward | rel_goal | velocity | done | flags and the five host destinations are adjacent in the same order
- * (one 22*N-byte block each), a single device-to-host copy is issued instead of five.                */
+/* Host-buffer step (the reference-facing call with HOST memory): actions_host i64[N] in, reward f32[N], done u8[N],
+ * flags u8[N], rel_goal f32[N][2] and velocity f32[N][2] out (any out pointer may be NULL); returns when the results are
+ * in the host buffers.  The local_map observation stays on the device.
+ *   - Fast path: the five bound device outputs are adjacent in memory in the order reward | rel_goal | velocity | done |
+ *     flags, the five host destinations are adjacent in the same order (one 22*N-byte block each, 16-byte aligned, N even)
+ *     and the host block is pinned (cudaHostAlloc / cudaHostRegister).  Then a small kernel queued behind the step writes
+ *     the host block directly and publishes a completion word in mapped memory which the call spins on: no copy engine,
+ *     no stream synchronisation.  Pinned action buffers are read in place by the step kernel.
+ *   - Otherwise: cudaMemcpyAsync in, step, cudaMemcpyAsync out (one copy when both blocks are packed), stream sync.
+ * FFMP_HOST_IO in the environment at ffmp_create selects the path: 0 copy engines, 1 mapped results with copied
+ * actions, 2 (default) mapped results and in-place actions.
+ * ffmp_step_host = ffmp_step_host_async + ffmp_step_host_wait (gym.vector's step_async / step_wait): the host may
+ * work between the two; exactly one wait per async.                                                             */
 int ffmp_step_host(ffmp_handle *h, const int64_t *actions_host, float *reward_host, uint8_t *done_host,
                    uint8_t *flags_host, float *rel_goal_host, float *velocity_host, void *stream);
+int ffmp_step_host_async(ffmp_handle *h, const int64_t *actions_host, float *reward_host, uint8_t *done_host,
+                         uint8_t *flags_host, float *rel_goal_host, float *velocity_host, void *stream);
+int ffmp_step_host_wait(ffmp_handle *h);
 
 /* Per-kernel device timing (CUDA events recorded by the library on the launching streams).  enable != 0: start
  * recording the next (at most 256) ticks.  enable == 0: stop, synchronise the recorded events and return the

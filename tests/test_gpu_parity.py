@@ -291,6 +291,55 @@ def test_rollout_api_and_host_step(ffmp, cuda_device):
     env.close()
 
 
+@pytest.mark.parametrize("host_io,pinned", [(0, True), (1, True), (2, True), (2, False)])
+def test_host_step_paths(ffmp, cuda_device, monkeypatch, host_io, pinned):
+    """ffmp_step_host through the copy engines (FFMP_HOST_IO=0), with the results written to pinned host memory by the
+    export kernel (1), with the actions read in place as well (2), and with pageable buffers (falls back to copies):
+    200 steps with auto-resets, every host-side result bit-compared with the oracle; step_async / step_wait split."""
+    monkeypatch.setenv("FFMP_HOST_IO", str(host_io))
+    N = 64
+    env = ffmp.FFMPVectorEnv(N, seed=31, grid=64, window=32, max_steps=20)
+    orc = oracle.OracleVectorEnv(N, seed=31, grid=64, window=32, max_steps=20)
+    if not pinned:      # pageable result block with the packed layout
+        block = torch.zeros((22 * N + 16,), dtype=torch.uint8)
+        r, g, v, dn, fl = env._split_out_block(block, N)
+        env._host = {"reward": r, "rel_goal": g, "velocity": v, "done": dn, "flags": fl, "done_bool": dn.view(torch.bool), "info": {"flags": fl}}
+        import ctypes as C
+        env._host_ptrs = tuple(C.c_void_p(env._host[k].data_ptr()) for k in ("reward", "done", "flags", "rel_goal", "velocity"))
+    env.reset(); orc.reset()
+    rng = np.random.default_rng(8)
+    bufs = [torch.zeros(N, dtype=torch.int64) for _ in range(3)]
+    if pinned:
+        bufs = [b.pin_memory() for b in bufs]
+    ndone = 0
+    for t in range(200):
+        a = bufs[t % 3]
+        a.copy_(torch.as_tensor(rng.integers(0, 28, N)))
+        if t % 2:
+            obs, reward, done, info = env.step_host(a)
+        else:
+            env.step_async(a)
+            obs, reward, done, info = env.step_wait()
+        orc.step(a.numpy())
+        assert reward.device.type == "cpu"
+        assert np.array_equal(reward.numpy().view(np.uint32), orc.reward.view(np.uint32)), t
+        assert np.array_equal(done.numpy().astype(np.uint8), orc.done), t
+        assert np.array_equal(info["flags"].numpy(), orc.flags), t
+        assert np.array_equal(obs["relative_goal"].numpy().view(np.uint32), orc.rel_goal.view(np.uint32)), t
+        assert np.array_equal(obs["velocity"].numpy().view(np.uint32), orc.velocity.view(np.uint32)), t
+        ndone += int(orc.done.sum())
+        if t % 20 == 19:
+            compare_env(env, orc, t)
+    assert ndone > 100 and env.error_word() == 0
+    # a second wait without an async is a no-op; two asyncs without a wait are refused
+    assert env._L.ffmp_step_host_wait(env._h) == 0
+    env.step_async(bufs[0])
+    with pytest.raises(ffmp.native.NativeError):
+        env.step_async(bufs[1])
+    env.step_wait()
+    env.close()
+
+
 def test_invalid_actions_and_errors(ffmp, cuda_device):
     env = ffmp.FFMPVectorEnv(4, seed=1, grid=64, window=32)
     with pytest.raises(ffmp.native.NativeError):
