@@ -629,6 +629,37 @@ int ffmp_learner_input(ffmp_handle *h, void *out_dev, int32_t dtype, float scale
     return FFMP_OK;
 }
 
+int ffmp_scan(ffmp_handle *h, int32_t beams, float range_max, float *scan_dev, uint8_t *hit_dev, void *stream) {
+    if (!h || !scan_dev) return fail(FFMP_ERR_ARG, "null argument");
+    if (!h->ready) return fail(FFMP_ERR_STATE, "ffmp_reset must be called before ffmp_scan");
+    if (beams <= 0 || beams > 65536 || !(range_max > 0.0f)) return fail(FFMP_ERR_ARG, "beams must be in [1,65536] and range_max > 0");
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the scenario slot an env has just switched to may still be regenerating for a *later* episode only: the current
+    // slot is complete by construction (run_tick waits for it), so no join is needed here
+    ffmp::ScanArgs a{};
+    a.n = h->cfg.num_envs; a.G = h->cfg.grid; a.beams = beams; a.range_max = range_max; a.flow_mode = 1;
+    a.map = h->b.flow; a.state = h->b.state; a.S = h->cfg.slots; a.N = h->cfg.num_envs;
+    a.scan = scan_dev; a.hit = hit_dev;
+    CK(ffmp::launch_scan(a, st));
+    h->launches += 1;
+    return FFMP_OK;
+}
+
+int ffmp_op_scan(int32_t device, int32_t n, int32_t G, const uint8_t *map_dev, int32_t flow_mode, const float *pose_dev,
+                 int32_t beams, float range_max, float *scan_dev, uint8_t *hit_dev, void *stream) {
+    if (n < 0 || !map_dev || !pose_dev || !scan_dev) return fail(FFMP_ERR_ARG, "bad argument");
+    if (G < 1 || G > 32768) return fail(FFMP_ERR_ARG, "G out of range");
+    if (beams <= 0 || beams > 65536 || !(range_max > 0.0f)) return fail(FFMP_ERR_ARG, "beams must be in [1,65536] and range_max > 0");
+    if (int rc = check_device(device)) return rc;
+    DeviceGuard guard(device);
+    ffmp::ScanArgs a{};
+    a.n = n; a.G = G; a.beams = beams; a.range_max = range_max; a.flow_mode = flow_mode ? 1 : 0;
+    a.map = map_dev; a.pose = pose_dev; a.scan = scan_dev; a.hit = hit_dev;
+    CK(ffmp::launch_scan(a, static_cast<cudaStream_t>(stream)));
+    return FFMP_OK;
+}
+
 int ffmp_join(ffmp_handle *h, void *stream) {
     if (!h) return fail(FFMP_ERR_ARG, "handle is null");
     DeviceGuard guard(h->cfg.device);

@@ -86,6 +86,18 @@ struct FeedArgs {
     void *out;                  // f32 or bf16 [N][2][W][W]
 };
 
+struct ScanArgs {
+    int n, G, beams;
+    float range_max;
+    int flow_mode;              // 1: map is a flow image (255 = occupied), 0: an occupancy plane (non-zero = occupied)
+    const uint8_t *map;         // u8 planes [..][G][G]
+    const float *pose;          // f32[n][3] (operator: plane = item) or null (env: pose and plane from the state records)
+    const uint32_t *state;      // env: [N][16]
+    int S, N;                   // env: plane = (episode % S) * N + env
+    float *scan;                // f32[n][beams]
+    uint8_t *hit;               // u8[n] is_collision2 of the beam list, or null
+};
+
 struct HostExportArgs {
     const void *src;            // dev: packed result block (reward | rel_goal | velocity | done | flags), 16-byte aligned
     void *dst;                  // device-visible address of the caller's pinned host block, 16-byte aligned
@@ -97,6 +109,7 @@ struct HostExportArgs {
 
 // launchers (each returns the cudaError_t of the launch)
 cudaError_t launch_host_export(const HostExportArgs &a, cudaStream_t st);   // host_io.cu: programmatic dependent of the tick
+cudaError_t launch_scan(const ScanArgs &a, cudaStream_t st);                // scan.cu
 cudaError_t launch_learner_input(const FeedArgs &a, cudaStream_t st);
 cudaError_t launch_scenarios(const ScenarioArgs &a, int grid, cudaStream_t st);
 cudaError_t launch_flow_field(const FlowArgs &a, int grid, cudaStream_t st);

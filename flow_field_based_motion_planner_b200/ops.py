@@ -3,6 +3,7 @@
   generate_scenarios -> replaces the episode_manager node   (/root/reference/src/train.py:86-90,128-132)
   flow_field         -> replaces the /bev/* flow-image node  (/root/reference/src/train.py:84,116-121)
   rewarder           -> batched FFMP.rewarder                (/root/reference/src/gym_ffmp/envs/ffmp.py:167-176)
+  scan               -> replaces Gazebo's /scan LaserScan    (/root/reference/src/train.py:87,144-150; SPEC.md §9)
 No CPU fallback: every function raises if the CUDA library or a B200 is missing.
 """
 import ctypes as C
@@ -63,6 +64,26 @@ def flow_field(occ, goal_cells, want_cost=True):
                                           C.c_void_p(flow.data_ptr()), C.c_void_p(ws.data_ptr()), _stream(occ.device)),
                      "ffmp_op_flow_field")
     return (cost if want_cost else None), flow
+
+
+def scan(grid_map, pose, beams=360, range_max=3.5, flow_mode=True):
+    """LiDAR scan synthesis (SPEC.md §9): grid_map u8[n,G,G] (flow image if flow_mode else occupancy plane), pose f32[n,3]
+    -> (ranges f32[n,beams] in metres, +inf = no return, 0 = robot cell occupied; hit u8[n] = FFMP.is_collision2)."""
+    L = native.lib()
+    dev = _dev_index(grid_map)
+    assert grid_map.dtype == torch.uint8 and grid_map.dim() == 3 and grid_map.shape[1] == grid_map.shape[2]
+    m = grid_map.contiguous()
+    n, G = m.shape[0], m.shape[1]
+    p = pose.to(device=m.device, dtype=torch.float32).contiguous()
+    assert p.shape == (n, 3)
+    out = torch.empty((n, beams), dtype=torch.float32, device=m.device)
+    hit = torch.empty((n,), dtype=torch.uint8, device=m.device)
+    if n:
+        with torch.cuda.device(m.device):
+            native.check(L.ffmp_op_scan(dev, n, G, C.c_void_p(m.data_ptr()), 1 if flow_mode else 0, C.c_void_p(p.data_ptr()),
+                                        int(beams), C.c_float(range_max), C.c_void_p(out.data_ptr()),
+                                        C.c_void_p(hit.data_ptr()), _stream(m.device)), "ffmp_op_scan")
+    return out, hit
 
 
 def flow_dir(flow):

@@ -271,6 +271,19 @@ class FFMPVectorEnv:
                                                     C.c_float(scale), self._stream()), "ffmp_learner_input")
         return out
 
+    def scan(self, beams=360, range_max=3.5, out=None):
+        """LiDAR scan of every env at its current pose on its current scenario (SPEC.md §9; the `/scan` input of
+        FFMP.rewarder2, train.py:87,144-150,577) -> (ranges f32[N,beams], hit u8[N] = is_collision2 of the beams)."""
+        N = self.num_envs
+        if out is None:
+            out = torch.empty((N, beams), dtype=torch.float32, device=self.device)
+        assert out.dtype == torch.float32 and out.device == self.device and out.is_contiguous() and out.numel() == N * beams
+        hit = torch.empty((N,), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            native.check(self._L.ffmp_scan(self._h, int(beams), C.c_float(range_max), C.c_void_p(out.data_ptr()),
+                                           C.c_void_p(hit.data_ptr()), self._stream()), "ffmp_scan")
+        return out, hit
+
     def join(self):
         """Order the current stream after all queued background scenario regeneration."""
         with torch.cuda.device(self.device):

@@ -158,6 +158,11 @@ int ffmp_obs_slot(const ffmp_handle *h, int32_t *newest_slot);
  * times `scale` (1.0 = the reference's plain float cast).  out_dev: caller-allocated device memory, 16-byte aligned.   */
 int ffmp_learner_input(ffmp_handle *h, void *out_dev, int32_t dtype, float scale, void *stream);
 
+/* LiDAR scan synthesis (SPEC.md §9) on every env's current scenario and pose: scan f32[N][beams] ranges in metres
+ * (+inf = no return within range_max, 0 = robot cell occupied), hit u8[N] = FFMP.is_collision2 of the beam list (may be
+ * NULL).  Replaces the /scan LaserScan the reference fed to rewarder2 (src/train.py:87,144-150,577; ffmp.py:108-117). */
+int ffmp_scan(ffmp_handle *h, int32_t beams, float range_max, float *scan_dev, uint8_t *hit_dev, void *stream);
+
 /* Make `stream` wait (device-side, no host sync) for all queued background regeneration. */
 int ffmp_join(ffmp_handle *h, void *stream);
 
@@ -179,6 +184,11 @@ int ffmp_op_scenarios(int32_t device, int32_t n, int32_t G, uint32_t p_thresh, i
 size_t ffmp_op_flow_field_workspace(int32_t n, int32_t G);
 int ffmp_op_flow_field(int32_t device, int32_t n, int32_t G, const uint8_t *occ_dev, const int32_t *goal_cells_dev,
                        int32_t *cost_dev, uint8_t *flow_dev, void *workspace_dev, void *stream);
+
+/* Stateless LiDAR scan synthesis (SPEC.md §9): map u8[n][G][G] (flow_mode 1: flow image, 255 = occupied; 0: occupancy
+ * plane, non-zero = occupied), pose f32[n][3] (x, y, yaw) -> scan f32[n][beams], hit u8[n] (may be NULL).       */
+int ffmp_op_scan(int32_t device, int32_t n, int32_t G, const uint8_t *map_dev, int32_t flow_mode, const float *pose_dev,
+                 int32_t beams, float range_max, float *scan_dev, uint8_t *hit_dev, void *stream);
 
 /* Batched FFMP.rewarder (ffmp.py:167-176) on caller-supplied ego-centred local maps:
  * local_map i32[n][W][W] (>0 = occupied, robot at (W/2,W/2)), rel_goal f32[n][2], is_first u8[n],

@@ -50,6 +50,7 @@ def lib():
             "orc_flow_field": (None, [u8p, C.c_int, C.c_int, C.c_int, i32p, u8p, u8p]),
             "orc_crop": (None, [u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]),
             "orc_collision": (C.c_int, [u8p, C.c_int, C.c_int, C.c_int]),
+            "orc_scan": (C.c_int, [u8p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, f32p]),
             "orc_env_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.c_uint32, C.c_float, C.c_int]),
             "orc_env_destroy": (None, [C.c_void_p]),
             "orc_env_reset": (None, [C.c_void_p]),
@@ -117,6 +118,15 @@ def crop(flow, W, ci, cj):
     return out
 
 
+def scan(grid_map, pose, beams=360, range_max=3.5, flow_mode=True):
+    """SPEC.md §9: (ranges f32[beams], is_collision2 flag) of one pose on a flow image (flow_mode) or an occupancy plane."""
+    m = np.ascontiguousarray(grid_map, np.uint8)
+    out = np.zeros(beams, np.float32)
+    hit = lib().orc_scan(_ptr(m, C.c_uint8), 1 if flow_mode else 0, m.shape[0], np.float32(pose[0]), np.float32(pose[1]),
+                         np.float32(pose[2]), beams, np.float32(range_max), _ptr(out, C.c_float))
+    return out, int(hit)
+
+
 def sincos(a):
     s, c = C.c_float(), C.c_float()
     lib().orc_sincos(np.float32(a), C.byref(s), C.byref(c))
@@ -154,6 +164,14 @@ class OracleVectorEnv:
         a = np.ascontiguousarray(actions, np.int64)
         self._L.orc_env_step(self._h, _ptr(a, C.c_int64))
         return self.obs(), self.reward, self.done, self.flags
+
+    def scan(self, beams=360, range_max=3.5):
+        """SPEC.md §9 on every env's current scenario and pose: (ranges f32[N,beams], hit u8[N])."""
+        out = np.zeros((self.N, beams), np.float32)
+        hit = np.zeros(self.N, np.uint8)
+        for n in range(self.N):
+            out[n], hit[n] = scan(self.flow[n], self.pose[n], beams, range_max, True)
+        return out, hit
 
     def obs(self):
         return {"local_map": self.local_map, "relative_goal": self.rel_goal, "velocity": self.velocity}

@@ -11,7 +11,7 @@
  *     by executing the unmodified reference (oracle/make_golden.py).
  *   - the remaining functions implement the [SPEC] parts the reference does not contain
  *     (hash map generator, BFS integration field, 8-neighbour argmin, fp32 unicycle, crop,
- *     step/reset sequencing).  For those rows parity is UNPINNED against the reference
+ *     step/reset sequencing, LiDAR scan synthesis).  For those rows parity is UNPINNED against the reference
  *     (SURVEY.md §0/§8c): they are pinned only by SPEC.md and by oracle<->CUDA equality.
  *
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math -shared -fPIC (see oracle/build.py).
@@ -309,6 +309,51 @@ int orc_collision(const uint8_t *flow, int G, int ci, int cj) {
             if (flow[i * G + j] == 255) return 1;
         }
     return 0;
+}
+
+/* [SPEC] §9 LiDAR scan synthesis: B beams through the grid (exact cell traversal), one fp32 rounding per operation.
+ * map: flow image (flow_mode 1: 255 = occupied) or occupancy plane (flow_mode 0: non-zero = occupied).
+ * Returns is_collision2 of the beam list (ffmp.py:108-117: a non-zero range below 0.13). */
+static int scan_blocked(const uint8_t *map, int flow_mode, int G, int i, int j) {
+    if (i < 0 || j < 0 || i >= G || j >= G) return 1;
+    return flow_mode ? map[i * G + j] == 255 : map[i * G + j] != 0;
+}
+
+int orc_scan(const uint8_t *map, int flow_mode, int G, float x, float y, float yaw, int beams, float range_max,
+             float *out) {
+    const float inc = TWO_PI_F / (float)beams;
+    const float u0 = x * INV_RES + 0.5f, v0 = y * INV_RES + 0.5f;
+    const int i0 = (int)floorf(u0), j0 = (int)floorf(v0);
+    int hit = 0;
+    if (scan_blocked(map, flow_mode, G, i0, j0)) {
+        for (int k = 0; k < beams; k++) out[k] = 0.0f;
+        return 0;
+    }
+    const float fu = u0 - floorf(u0), fv = v0 - floorf(v0);
+    const float max_t = range_max * INV_RES;
+    for (int k = 0; k < beams; k++) {
+        float s, c;
+        orc_sincos(orc_pi_to_pi(yaw + (float)k * inc), &s, &c);
+        int si, sj, i = i0, j = j0;
+        float tdx, tmx, tdy, tmy;
+        if (c > 0.0f) { si = 1; tdx = 1.0f / c; tmx = (1.0f - fu) * tdx; }
+        else if (c < 0.0f) { si = -1; tdx = 1.0f / (-c); tmx = fu * tdx; }
+        else { si = 0; tdx = tmx = INFINITY; }
+        if (s > 0.0f) { sj = 1; tdy = 1.0f / s; tmy = (1.0f - fv) * tdy; }
+        else if (s < 0.0f) { sj = -1; tdy = 1.0f / (-s); tmy = fv * tdy; }
+        else { sj = 0; tdy = tmy = INFINITY; }
+        float r;
+        for (;;) {
+            float t;
+            if (tmx < tmy) { t = tmx; i += si; tmx = tmx + tdx; }
+            else { t = tmy; j += sj; tmy = tmy + tdy; }
+            if (t > max_t) { r = INFINITY; break; }
+            if (scan_blocked(map, flow_mode, G, i, j)) { r = t * RES; break; }
+        }
+        out[k] = r;
+        if (r != 0.0f && (double)r < 0.13) hit = 1;
+    }
+    return hit;
 }
 
 /* ------------------------------------------------------------------------------------------

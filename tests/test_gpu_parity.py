@@ -472,3 +472,75 @@ def test_learner_input_matches_float_cast(ffmp, cuda_device):
         assert torch.equal(env.learner_input(dtype=torch.bfloat16).float(), want)
         assert torch.allclose(env.learner_input(scale=1.0 / 255.0), want / 255.0, rtol=0, atol=1e-7)
     env.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# L: LiDAR scan synthesis (SPEC.md §9)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("G,beams,rmax,flow_mode", [(128, 360, 3.5, True), (64, 7, 1.0, False), (100, 1000, 10.0, True), (32, 1, 3.5, False)])
+def test_scan_operator_bit_exact(ffmp, cuda_device, G, beams, rmax, flow_mode):
+    rng = np.random.default_rng(G + beams)
+    n = 24
+    maps, poses = [], []
+    for k in range(n):
+        occ, start, goal, cells = oracle.scenario(5, k, 1, G, p_occ=0.15)
+        if flow_mode:
+            _, _, m = oracle.flow_field(occ, cells[2], cells[3])
+        else:
+            m = occ * np.uint8(rng.integers(1, 255))          # any non-zero value is occupied
+        maps.append(m)
+        if k % 6 == 5:      # anywhere, including occupied cells, the border and outside the grid
+            poses.append([rng.uniform(-0.3, G * 0.05 + 0.3), rng.uniform(-0.3, G * 0.05 + 0.3), rng.uniform(-3.14, 3.14)])
+        else:               # a free cell, off-centre
+            free = np.argwhere(occ == 0)
+            i, j = free[rng.integers(0, len(free))]
+            poses.append([i * 0.05 + rng.uniform(-0.024, 0.024), j * 0.05 + rng.uniform(-0.024, 0.024), rng.uniform(-3.14, 3.14)])
+    poses[0][2] = 0.0                                          # axis-aligned beams (a direction cosine of exactly 0 / 1)
+    poses[1] = [float(np.float32(5 * 0.05)), float(np.float32(7 * 0.05)), float(np.float32(np.pi / 2))]
+    maps_n, poses_n = np.stack(maps), np.array(poses, np.float32)
+    scan, hit = ffmp.ops.scan(torch.as_tensor(maps_n, device=cuda_device), torch.as_tensor(poses_n, device=cuda_device),
+                              beams=beams, range_max=rmax, flow_mode=flow_mode)
+    scan, hit = t2n(scan), t2n(hit)
+    for k in range(n):
+        er, eh = oracle.scan(maps_n[k], poses_n[k], beams, rmax, flow_mode)
+        assert np.array_equal(scan[k].view(np.uint32), er.view(np.uint32)), k
+        assert hit[k] == eh, k
+    assert (scan > 0).any()
+
+
+def test_scan_generic_kernel_matches_windowed(ffmp, cuda_device, monkeypatch):
+    """FFMP_SCAN_GENERIC=1 forces the global-load kernel (used for range_max beyond the shared-memory window)."""
+    env = ffmp.FFMPVectorEnv(16, seed=2, grid=128, window=100)
+    env.reset()
+    a, ha = env.scan(360, 3.5)
+    monkeypatch.setenv("FFMP_SCAN_GENERIC", "1")
+    b, hb = env.scan(360, 3.5)
+    assert torch.equal(a.view(torch.int32), b.view(torch.int32)) and torch.equal(ha, hb)
+    env.close()
+
+
+def test_scan_env_rollout_and_rewarder2(ffmp, cuda_device):
+    """env.scan() at every step of a rollout equals the oracle's scan of the oracle env's pose and flow image, and feeding
+    it to the batched FFMP.rewarder2 gives the collision flag the reference function computes from the same list."""
+    N = 32
+    env = ffmp.FFMPVectorEnv(N, seed=17, grid=128, window=100)
+    orc = oracle.OracleVectorEnv(N, seed=17, grid=128, window=100)
+    env.reset(); orc.reset()
+    rng = np.random.default_rng(3)
+    hits = 0
+    for t in range(60):
+        a = rng.integers(0, 28, N)
+        env.step(torch.as_tensor(a, device=cuda_device)); orc.step(a)
+        scan, hit = env.scan(beams=360, range_max=3.5)
+        es, eh = orc.scan(360, 3.5)
+        assert np.array_equal(t2n(scan).view(np.uint32), es.view(np.uint32)), t
+        assert np.array_equal(t2n(hit), eh), t
+        hits += int(eh.sum())
+        if t % 20 == 0:
+            # rewarder2 takes f64 ranges with NaN = None: drop inf / 0 as the trainer's callback does (train.py:144-150)
+            s64 = scan.double()
+            s64 = torch.where(torch.isinf(s64) | (s64 == 0), torch.full_like(s64, float("nan")), s64)
+            d_first = torch.zeros(N, dtype=torch.float32, device=cuda_device)
+            reward, done, flags = ffmp.ops.rewarder2(s64, env.rel_goal, torch.ones(N, dtype=torch.uint8, device=cuda_device), d_first)
+            assert np.array_equal(t2n(flags) & 1, eh), t
+    env.close()

@@ -117,3 +117,73 @@ def test_episode_semantics():
     assert (env.episode == 1).all() and (env.steps == 0).all()
     env.step(np.array([3, 99, -1, 27]))
     assert env.error_word & 1
+
+
+# ---------------------------------------------------------------------------------------------------
+# L: LiDAR scan synthesis (SPEC.md §9)
+# ---------------------------------------------------------------------------------------------------
+def _room(G):
+    occ = np.zeros((G, G), np.uint8)
+    occ[0, :] = occ[-1, :] = occ[:, 0] = occ[:, -1] = 1
+    return occ
+
+
+def test_scan_empty_room_axis_beams_are_exact():
+    """Robot on a cell centre of an empty walled room: the four axis beams end on the wall faces, (k + 0.5) cells away."""
+    G = 64
+    occ = _room(G)
+    r, hit = oracle.scan(occ, (1.6, 1.0, 0.0), beams=4, range_max=3.5, flow_mode=False)   # cell (32, 20)
+    assert hit == 0
+    assert r[0] == np.float32(np.float32(30.5) * np.float32(0.05))      # +x: wall row 63 begins at u = 63, u0 = 32.5
+    assert r[2] == np.float32(np.float32(31.5) * np.float32(0.05))      # -x: wall row 0 ends at u = 1
+    assert abs(r[1] - 42.5 * 0.05) < 1e-4 and abs(r[3] - 19.5 * 0.05) < 1e-4   # +-y (cos(pi/2) is ~-4e-8, not 0)
+    # beyond the sensor range nothing returns
+    r, _ = oracle.scan(occ, (1.6, 1.0, 0.0), beams=4, range_max=1.0, flow_mode=False)
+    assert np.isinf(r[0]) and np.isinf(r[1]) and np.isinf(r[2]) and r[3] == np.float32(np.float32(19.5) * np.float32(0.05))
+
+
+def test_scan_blocked_robot_cell_and_modes():
+    G = 32
+    occ = _room(G)
+    occ[10, 10] = 1
+    r, hit = oracle.scan(occ, (0.5, 0.5, 0.3), beams=16, flow_mode=False)     # robot cell (10, 10) is occupied
+    assert (r == 0).all() and hit == 0                                        # zeros are "no reading" (train.py:146)
+    r, hit = oracle.scan(occ, (-1.0, 0.5, 0.0), beams=16, flow_mode=False)    # out of the grid
+    assert (r == 0).all() and hit == 0
+    # a flow image (255 = occupied, other values are direction codes) gives the same scan as its occupancy plane
+    cost, d, flow = oracle.flow_field(occ, 20, 20)
+    a, ha = oracle.scan(occ, (0.8, 0.7, 1.0), beams=90, flow_mode=False)
+    b, hb = oracle.scan(flow, (0.8, 0.7, 1.0), beams=90, flow_mode=True)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and ha == hb
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_scan_hits_first_occupied_cell_along_the_ray(seed):
+    """Independent fp64 check: the ray is free up to the reported range and blocked just beyond it."""
+    G = 128
+    occ, start, goal, cells = oracle.scenario(seed, 3, 0, G)
+    rng = np.random.default_rng(seed)
+    free = np.argwhere(occ == 0)
+    B = 72
+    for (i, j) in free[rng.integers(0, len(free), 12)]:
+        x, y, yaw = np.float32(i * 0.05 + rng.uniform(-0.02, 0.02)), np.float32(j * 0.05 + rng.uniform(-0.02, 0.02)), np.float32(rng.uniform(-3.1, 3.1))
+        r, hit = oracle.scan(occ, (x, y, yaw), beams=B, range_max=3.5, flow_mode=False)
+        inc = 2 * np.pi / B
+        for k in range(B):
+            th = float(yaw) + k * inc
+            c, s = np.cos(th), np.sin(th)
+            def blocked(t):
+                u, v = float(x) * 20 + 0.5 + t * 20 * c, float(y) * 20 + 0.5 + t * 20 * s
+                ii, jj = int(np.floor(u)), int(np.floor(v))
+                return not (0 <= ii < G and 0 <= jj < G) or occ[ii, jj] != 0
+            if np.isinf(r[k]):
+                ts = np.arange(0.0, 3.5 - 2e-3, 0.004)
+            else:
+                assert 0 < r[k] <= 3.5 + 1e-5
+                ts = np.arange(0.0, max(0.0, float(r[k]) - 2e-3), 0.004)
+                assert blocked(float(r[k]) + 2e-3), (i, j, k)
+            assert not any(blocked(t) for t in ts), (i, j, k)
+        # hit == the reference's is_collision2 on the list the trainer would keep (finite, non-zero ranges)
+        kept = np.array([v for v in r if np.isfinite(v) and v != 0], np.float64)
+        ref = oracle.lib().orc_ref_is_collision2(kept.ctypes.data_as(oracle.C.POINTER(oracle.C.c_double)), len(kept)) if len(kept) else 0
+        assert hit == ref

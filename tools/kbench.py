@@ -76,6 +76,15 @@ def main():
         med, _ = timed(lambda: env.learner_input(dtype=dt, out=out))
         res[f"learner_input_{nm}_us"] = med * 1e3
         res[f"learner_input_{nm}_frac"] = N * 2 * W * W * (1 + wb) / (med * 1e-3) / 6549.8e9
+    # LiDAR scan synthesis (SPEC §9) of every env at its current pose: 360 beams, 3.5 m
+    sc_out = torch.empty((N, 360), dtype=torch.float32, device=dev)
+    med, best = timed(lambda: env.scan(360, 3.5, out=sc_out))
+    res["scan360_us"], res["scan360_best_us"] = med * 1e3, best * 1e3
+    sc = env.scan(360, 3.5, out=sc_out)[0]
+    fin = torch.isfinite(sc)
+    res["scan360_beams_per_s"] = N * 360 / (med * 1e-3)
+    res["scan360_mean_range_m"] = float(sc[fin].mean().item())
+    res["scan360_no_return_frac"] = float((~fin).float().mean().item())
     acts = torch.randint(0, 28, (250, N), device=dev)
     for _ in range(2):
         env.rollout(acts)
