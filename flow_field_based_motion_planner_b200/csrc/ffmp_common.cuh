@@ -180,6 +180,54 @@ __device__ __forceinline__ uint32_t scenario_free_word(uint32_t key, int R, int 
     return fr & col_range_mask(1, G - 2, c0);                               // border columns / padding
 }
 
+// Column-interleaved form of the same row (rows of up to 128 cells as 4 words: word w bit b <-> column 4b + w), used by the
+// G <= 128 flow-field kernel.  Columns lo..hi (inclusive) as a mask of word w:
+__device__ __forceinline__ uint32_t il_col_range_mask(int lo, int hi, int w) {
+    int blo = (lo - w + 3) >> 2, bhi = (hi - w) >> 2;      // ceil / floor of (col - w) / 4 (arithmetic shifts)
+    blo = max(blo, 0); bhi = min(bhi, 31);
+    if (blo > bhi) return 0u;
+    return (0xFFFFFFFFu >> (31 - bhi)) & (0xFFFFFFFFu << blo);
+}
+
+__device__ __forceinline__ void scenario_free_row_il(uint32_t key, int R, int G, int bs, uint32_t p_thresh,
+                                                     const ScenarioParams &p, uint32_t (&out)[4]) {
+    if (R <= 0 || R >= G - 1) {                                             // border rows / padding rows
+        out[0] = out[1] = out[2] = out[3] = 0u;
+        return;
+    }
+    const uint32_t rblk = static_cast<uint32_t>(R >> bs) << 16;
+    uint32_t occ[4];
+    if (bs >= 2) {
+        // the block column of column 4b + w is b >> (bs - 2) for every w: one occupancy word serves the four words
+        const int sb = bs - 2;
+        uint32_t o = 0;
+        if (sb >= 5) {
+            o = mix32(key + rblk * 0x9E3779B1u) < p_thresh ? 0xFFFFFFFFu : 0u;
+        } else {
+            const int bw = 1 << sb;
+            const uint32_t bmask = (1u << bw) - 1u;
+            for (int b = 0; b < 32; b += bw)
+                if (mix32(key + (rblk | static_cast<uint32_t>(b >> sb)) * 0x9E3779B1u) < p_thresh) o |= bmask << b;
+        }
+        occ[0] = occ[1] = occ[2] = occ[3] = o;
+    } else {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            uint32_t o = 0;
+            for (int b = 0; b < 32; ++b)
+                if (mix32(key + (rblk | static_cast<uint32_t>((4 * b + w) >> bs)) * 0x9E3779B1u) < p_thresh) o |= 1u << b;
+            occ[w] = o;
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        uint32_t fr = ~occ[w];
+        if (abs(R - p.si) <= 2) fr |= il_col_range_mask(p.sj - 2, p.sj + 2, w);   // cleared 5x5 around the start
+        if (abs(R - p.gi) <= 2) fr |= il_col_range_mask(p.gj - 2, p.gj + 2, w);   // ... and around the goal
+        out[w] = fr & il_col_range_mask(1, G - 2, w);                             // border columns / padding
+    }
+}
+
 // SPEC.md §1 action table (robot/config.py:25-58)
 __device__ __forceinline__ void action_lookup(int a, float &v, float &w) {
     const int iv = a / 7, iw = a - 7 * iv;

@@ -83,16 +83,37 @@ __device__ __forceinline__ void bytes4x4(uint32_t p0, uint32_t p1, uint32_t p2, 
     out[2] = __byte_perm(b, d, 0x5410); out[3] = __byte_perm(b, d, 0x7632);
 }
 
-// funnel shifts across the words of one row: value of the cell at column-1 / column+1 aligned to word w
-template <int WPR>
+// Neighbour columns of a row of WPR words: bit j of the result <- the cell at column-1 (from_lo) / column+1 (from_hi)
+// of the cell that bit j of word w stands for.
+//   linear layout (IL = false): word w holds columns 32w..32w+31 -> funnel shifts across the row words;
+//   column-interleaved layout (IL = true, WPR = 4): word w holds the columns c with c % 4 == w, bit b <-> column 4b + w.
+//   The horizontal neighbours of word w are then simply words w-1 / w+1 (register renames, no instruction); only the
+//   wrap-around words need a plain shift: 2 shifts per row instead of 8 funnel shifts.
+template <int WPR, bool IL = false>
 __device__ __forceinline__ uint32_t from_lo(const uint32_t (&x)[WPR], int w) {   // bit j <- cell j-1
-    return w > 0 ? __funnelshift_l(x[w - 1], x[w], 1) : x[w] << 1;
+    if constexpr (IL) return w > 0 ? x[w - 1] : x[WPR - 1] << 1;
+    else return w > 0 ? __funnelshift_l(x[w - 1], x[w], 1) : x[w] << 1;
 }
-template <int WPR>
+template <int WPR, bool IL = false>
 __device__ __forceinline__ uint32_t from_hi(const uint32_t (&x)[WPR], int w) {   // bit j <- cell j+1
-    return w + 1 < WPR ? __funnelshift_r(x[w], x[w + 1], 1) : x[w] >> 1;
+    if constexpr (IL) return w + 1 < WPR ? x[w + 1] : x[0] >> 1;
+    else return w + 1 < WPR ? __funnelshift_r(x[w], x[w + 1], 1) : x[w] >> 1;
 }
 
+// one delta swap: exchange the bits selected by m with the bits d positions above them
+__device__ __forceinline__ uint32_t delta_swap(uint32_t x, uint32_t m, int d) {
+    const uint32_t t = (x ^ (x >> d)) & m;
+    return x ^ t ^ (t << d);
+}
+// 8 nibbles -> 4 bytes: bit 4q + w -> bit 8w + q (index-bit rotation as four delta swaps), and its inverse
+__device__ __forceinline__ uint32_t nibbles_to_bytes(uint32_t x) {
+    x = delta_swap(x, 0x22222222u, 1); x = delta_swap(x, 0x0A0A0A0Au, 3);
+    x = delta_swap(x, 0x00CC00CCu, 6); return delta_swap(x, 0x0000F0F0u, 12);
+}
+__device__ __forceinline__ uint32_t bytes_to_nibbles(uint32_t x) {
+    x = delta_swap(x, 0x0000F0F0u, 12); x = delta_swap(x, 0x00CC00CCu, 6);
+    x = delta_swap(x, 0x0A0A0A0Au, 3); return delta_swap(x, 0x22222222u, 1);
+}
 // a - n (n subset of a) and x * m (m in {0,1}) forced onto the FMA pipe (IMAD) so that they do not compete with
 // the LOP3/SHF stream on the ALU pipe: the multipliers are runtime values ptxas cannot fold into IADD/LOP3/SEL.
 __device__ __forceinline__ uint32_t sub_on_fma(uint32_t a, uint32_t n, uint32_t neg1) {
@@ -122,6 +143,47 @@ __device__ __forceinline__ void flow_bytes32(uint32_t d0, uint32_t d1, uint32_t 
         transpose8(lo, hb);          // byte j of hb:lo = code of cell 8b+j, bit 7 = occupied
         out[2 * b] = ((lo & 0x0F0F0F0Fu) * 28u) | byte_sign_fill(lo);
         out[2 * b + 1] = ((hb & 0x0F0F0F0Fu) * 28u) | byte_sign_fill(hb);
+    }
+}
+
+// A row of 128 cells: linear words (word j = columns 32j..32j+31) <-> column-interleaved words (word w bit b = column 4b + w).
+// Interleaved word w, byte j = the bits w, w+4, .., w+28 of linear word j.
+__device__ __forceinline__ void row_to_interleaved(uint32_t (&x)[4]) {
+    uint32_t o[4];
+    bytes4x4(nibbles_to_bytes(x[0]), nibbles_to_bytes(x[1]), nibbles_to_bytes(x[2]), nibbles_to_bytes(x[3]), o);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) x[w] = o[w];
+}
+__device__ __forceinline__ void row_to_linear(uint32_t (&x)[4]) {
+    uint32_t o[4];
+    bytes4x4(x[0], x[1], x[2], x[3], o);        // the byte transpose is its own inverse
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = bytes_to_nibbles(o[j]);
+}
+
+// Interleaved row (4 words per plane) x (d0..d3 direction-code planes, occupied) -> the 128 flow bytes of the row in column
+// order, 32 words: byte planes -> per-word cell bytes (PRMT + 8x8 bit transposes) -> 4x4 byte transposes across the words.
+__device__ __forceinline__ void flow_bytes128_il(const uint32_t (&d0)[4], const uint32_t (&d1)[4], const uint32_t (&d2)[4],
+                                                 const uint32_t (&d3)[4], const uint32_t (&occ)[4], uint32_t (&out)[32]) {
+    uint32_t tl[4][4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) bytes4x4(d0[w], d1[w], d2[w], d3[w], tl[w]);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        uint32_t lo[4], hb[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            lo[w] = tl[w][b]; hb[w] = ((occ[w] >> (8 * b)) & 0xFFu) << 24;
+            transpose8(lo[w], hb[w]);      // byte j of hb:lo = code of the cell at bit 8b+j of word w, bit 7 = occupied
+        }
+        uint32_t x[4], y[4];
+        bytes4x4(lo[0], lo[1], lo[2], lo[3], x);   // x[j] = columns 4(8b+j) .. +3
+        bytes4x4(hb[0], hb[1], hb[2], hb[3], y);   // y[j] = columns 4(8b+4+j) .. +3
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            out[8 * b + j] = ((x[j] & 0x0F0F0F0Fu) * 28u) | byte_sign_fill(x[j]);
+            out[8 * b + 4 + j] = ((y[j] & 0x0F0F0F0Fu) * 28u) | byte_sign_fill(y[j]);
+        }
     }
 }
 
