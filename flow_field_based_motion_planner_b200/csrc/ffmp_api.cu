@@ -660,6 +660,176 @@ int ffmp_op_scan(int32_t device, int32_t n, int32_t G, const uint8_t *map_dev, i
     return FFMP_OK;
 }
 
+// ---- learner feed over peer memory (feed.cu) ------------------------------------------------------------------------
+struct ffmp_feed {
+    int device = 0, world = 1, rank = 0;
+    size_t block = 0, slot_stride = 0, buffer_stride = 0;
+    char *base = nullptr;                     // local allocation: header (4 KB) + 2 buffers x world slots
+    char *peer[ffmp::FEED_MAX_WORLD];         // base of rank r's allocation as mapped here (own rank: base)
+    bool opened[ffmp::FEED_MAX_WORLD];
+    uint32_t seq = 0;                         // sequence number of the latest local push
+    uint64_t launches = 0;
+
+    static constexpr size_t HDR = 4096, FLAG0 = 0, ACK0 = 1024, TICKET = 2048, ERRW = 2112, WORD_STRIDE = 64;
+    uint32_t *flag_in(int owner, int src) const { return reinterpret_cast<uint32_t *>(peer[owner] + FLAG0 + WORD_STRIDE * src); }
+    uint32_t *ack_in(int owner, int consumer) const { return reinterpret_cast<uint32_t *>(peer[owner] + ACK0 + WORD_STRIDE * consumer); }
+    uint32_t *ticket() const { return reinterpret_cast<uint32_t *>(base + TICKET); }
+    uint32_t *error_word() const { return reinterpret_cast<uint32_t *>(base + ERRW); }
+    char *slot_in(int owner, uint32_t sequence, int src) const {
+        return peer[owner] + HDR + (sequence & 1u) * buffer_stride + static_cast<size_t>(src) * slot_stride;
+    }
+};
+
+int ffmp_feed_create(int32_t device, int32_t world, int32_t rank, size_t block_bytes, ffmp_feed **out) {
+    if (!out) return fail(FFMP_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (world < 1 || world > ffmp::FEED_MAX_WORLD || rank < 0 || rank >= world || block_bytes == 0)
+        return fail(FFMP_ERR_ARG, "world must be in [1,16], rank in [0,world), block_bytes > 0");
+    if (int rc = check_device(device)) return rc;
+    DeviceGuard guard(device);
+    ffmp_feed *f = new (std::nothrow) ffmp_feed();
+    if (!f) return fail(FFMP_ERR_ARG, "out of host memory");
+    f->device = device; f->world = world; f->rank = rank; f->block = block_bytes;
+    f->slot_stride = align_up(block_bytes, 256);
+    f->buffer_stride = f->slot_stride * static_cast<size_t>(world);
+    for (int r = 0; r < ffmp::FEED_MAX_WORLD; ++r) { f->peer[r] = nullptr; f->opened[r] = false; }
+    const size_t total = ffmp_feed::HDR + 2 * f->buffer_stride;
+    void *p = nullptr;
+    cudaError_t ce = cudaMalloc(&p, total);
+    if (ce == cudaSuccess) ce = cudaMemset(p, 0, ffmp_feed::HDR);
+    if (ce != cudaSuccess) {
+        if (p) cudaFree(p);
+        delete f;
+        return fail(FFMP_ERR_CUDA, "feed allocation", ce);
+    }
+    f->base = static_cast<char *>(p);
+    f->peer[rank] = f->base;
+    *out = f;
+    return FFMP_OK;
+}
+
+int ffmp_feed_handle(ffmp_feed *f, uint8_t *handle_out) {
+    if (!f || !handle_out) return fail(FFMP_ERR_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "FFMP_IPC_HANDLE_BYTES");
+    DeviceGuard guard(f->device);
+    cudaIpcMemHandle_t hd;
+    CK(cudaIpcGetMemHandle(&hd, f->base));
+    std::memcpy(handle_out, &hd, sizeof(hd));
+    return FFMP_OK;
+}
+
+int ffmp_feed_connect(ffmp_feed *f, int32_t peer_rank, const uint8_t *handle) {
+    if (!f || !handle) return fail(FFMP_ERR_ARG, "null argument");
+    if (peer_rank < 0 || peer_rank >= f->world) return fail(FFMP_ERR_ARG, "peer rank out of range");
+    if (peer_rank == f->rank || f->opened[peer_rank]) return FFMP_OK;
+    DeviceGuard guard(f->device);
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, handle, sizeof(hd));
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    f->peer[peer_rank] = static_cast<char *>(p);
+    f->opened[peer_rank] = true;
+    return FFMP_OK;
+}
+
+int ffmp_feed_info(const ffmp_feed *f, void **base_dev, size_t *slot_stride, size_t *buffer_stride, uint32_t *seq) {
+    if (!f) return fail(FFMP_ERR_ARG, "feed is null");
+    if (base_dev) *base_dev = f->base + ffmp_feed::HDR;
+    if (slot_stride) *slot_stride = f->slot_stride;
+    if (buffer_stride) *buffer_stride = f->buffer_stride;
+    if (seq) *seq = f->seq;
+    return FFMP_OK;
+}
+
+int ffmp_feed_push(ffmp_handle *h, ffmp_feed *f, uint32_t dest_mask, double timeout_s, void *stream) {
+    if (!h || !f) return fail(FFMP_ERR_ARG, "null argument");
+    if (!h->ready) return fail(FFMP_ERR_STATE, "ffmp_reset must be called before ffmp_feed_push");
+    const ffmp_cfg &c = h->cfg;
+    const size_t N = c.num_envs, W = c.window;
+    if (f->block != N * (2 * W * W + 21)) return fail(FFMP_ERR_ARG, "feed block size does not match the env (N * (2 W^2 + 21))");
+    if ((2 * W * W) % 16 || reinterpret_cast<uintptr_t>(h->b.frames) % 16) return fail(FFMP_ERR_ARG, "2 W^2 must be a multiple of 16");
+    dest_mask &= f->world >= 32 ? 0xFFFFFFFFu : ((1u << f->world) - 1u);
+    for (int r = 0; r < f->world; ++r)
+        if (((dest_mask >> r) & 1u) && !f->peer[r]) return fail(FFMP_ERR_STATE, "destination rank is not connected (ffmp_feed_connect)");
+    DeviceGuard guard(f->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint32_t seq = ++f->seq;
+    // credit: the buffer of this parity was last used by push seq-2; every destination must have released it
+    if (seq > 2 && dest_mask) {
+        CK(ffmp::launch_feed_spin(reinterpret_cast<const uint32_t *>(f->base + ffmp_feed::ACK0), ffmp_feed::WORD_STRIDE / 4,
+                                  dest_mask, seq - 2, timeout_s, f->error_word(), st));
+        f->launches += 1;
+    }
+    ffmp::FeedPushArgs a{};
+    a.N = c.num_envs; a.K = c.ring; a.W = c.window; a.slot_new = h->p;
+    a.frames = h->b.frames; a.rel_goal = h->b.rel_goal; a.velocity = h->b.velocity; a.reward = h->b.reward; a.done = h->b.done;
+    a.ticket = f->ticket(); a.seq = seq;
+    int nd = 0;
+    for (int r = 0; r < f->world; ++r)
+        if ((dest_mask >> r) & 1u) {
+            a.dst[nd] = reinterpret_cast<uint8_t *>(f->slot_in(r, seq, f->rank));
+            a.flag[nd] = f->flag_in(r, f->rank);
+            ++nd;
+        }
+    a.ndst = nd;
+    CK(ffmp::launch_feed_push(a, st));
+    f->launches += 1;
+    return FFMP_OK;
+}
+
+int ffmp_feed_wait(ffmp_feed *f, uint32_t src_mask, double timeout_s, void **buffer_dev, void *stream) {
+    if (!f) return fail(FFMP_ERR_ARG, "feed is null");
+    if (f->seq == 0) return fail(FFMP_ERR_STATE, "ffmp_feed_push must be called before ffmp_feed_wait (SPMD: every rank pushes every step)");
+    DeviceGuard guard(f->device);
+    src_mask &= f->world >= 32 ? 0xFFFFFFFFu : ((1u << f->world) - 1u);
+    if (src_mask) {
+        CK(ffmp::launch_feed_spin(reinterpret_cast<const uint32_t *>(f->base + ffmp_feed::FLAG0), ffmp_feed::WORD_STRIDE / 4, src_mask,
+                                  f->seq, timeout_s, f->error_word(), static_cast<cudaStream_t>(stream)));
+        f->launches += 1;
+    }
+    if (buffer_dev) *buffer_dev = f->base + ffmp_feed::HDR + (f->seq & 1u) * f->buffer_stride;
+    return FFMP_OK;
+}
+
+int ffmp_feed_release(ffmp_feed *f, uint32_t src_mask, void *stream) {
+    if (!f) return fail(FFMP_ERR_ARG, "feed is null");
+    DeviceGuard guard(f->device);
+    src_mask &= f->world >= 32 ? 0xFFFFFFFFu : ((1u << f->world) - 1u);
+    ffmp::FeedTargets t{};
+    for (int r = 0; r < f->world; ++r) {
+        t.word[r] = nullptr;
+        if ((src_mask >> r) & 1u) {
+            if (!f->peer[r]) return fail(FFMP_ERR_STATE, "source rank is not connected (ffmp_feed_connect)");
+            t.word[r] = f->ack_in(r, f->rank);
+        }
+    }
+    if (src_mask) {
+        CK(ffmp::launch_feed_signal(t, src_mask, f->seq, static_cast<cudaStream_t>(stream)));
+        f->launches += 1;
+    }
+    return FFMP_OK;
+}
+
+int ffmp_feed_error(ffmp_feed *f, uint32_t *out, void *stream) {
+    if (!f || !out) return fail(FFMP_ERR_ARG, "null argument");
+    DeviceGuard guard(f->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaMemcpyAsync(out, f->error_word(), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return FFMP_OK;
+}
+
+int ffmp_feed_destroy(ffmp_feed *f) {
+    if (!f) return FFMP_OK;
+    DeviceGuard guard(f->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < f->world; ++r)
+        if (f->opened[r] && f->peer[r]) cudaIpcCloseMemHandle(f->peer[r]);
+    if (f->base) cudaFree(f->base);
+    delete f;
+    return FFMP_OK;
+}
+
 int ffmp_join(ffmp_handle *h, void *stream) {
     if (!h) return fail(FFMP_ERR_ARG, "handle is null");
     DeviceGuard guard(h->cfg.device);

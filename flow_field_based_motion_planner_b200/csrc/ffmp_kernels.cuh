@@ -98,6 +98,23 @@ struct ScanArgs {
     uint8_t *hit;               // u8[n] is_collision2 of the beam list, or null
 };
 
+constexpr int FEED_MAX_WORLD = 16;
+
+struct FeedTargets {
+    uint32_t *word[FEED_MAX_WORLD];   // word[r]: a flag / ack word in rank r's memory (peer mapped), or null
+};
+
+struct FeedPushArgs {
+    int N, K, W, slot_new, ndst;
+    const uint8_t *frames;            // [N][K][W][W] observation ring of this rank
+    const float *rel_goal, *velocity, *reward;
+    const uint8_t *done;
+    uint8_t *dst[FEED_MAX_WORLD];     // this rank's slot in the gather buffer of destination d (peer mapped or local)
+    uint32_t *flag[FEED_MAX_WORLD];   // flag word of this rank in destination d's memory
+    uint32_t *ticket;                 // local CTA completion counter (wraps to 0 by itself)
+    uint32_t seq;
+};
+
 struct HostExportArgs {
     const void *src;            // dev: packed result block (reward | rel_goal | velocity | done | flags), 16-byte aligned
     void *dst;                  // device-visible address of the caller's pinned host block, 16-byte aligned
@@ -109,6 +126,10 @@ struct HostExportArgs {
 
 // launchers (each returns the cudaError_t of the launch)
 cudaError_t launch_host_export(const HostExportArgs &a, cudaStream_t st);   // host_io.cu: programmatic dependent of the tick
+cudaError_t launch_feed_spin(const uint32_t *words, int stride_words, uint32_t mask, uint32_t want, double timeout_s,
+                             uint32_t *error_word, cudaStream_t st);         // feed.cu
+cudaError_t launch_feed_signal(const FeedTargets &t, uint32_t mask, uint32_t value, cudaStream_t st);
+cudaError_t launch_feed_push(const FeedPushArgs &a, cudaStream_t st);
 cudaError_t launch_scan(const ScanArgs &a, cudaStream_t st);                // scan.cu
 cudaError_t launch_learner_input(const FeedArgs &a, cudaStream_t st);
 cudaError_t launch_scenarios(const ScenarioArgs &a, int grid, cudaStream_t st);

@@ -14,6 +14,7 @@ COST_INF = 0x7FFFFFFF
 EXPORTS = [
     "ffmp_last_error", "ffmp_abi_version", "ffmp_query_sizes", "ffmp_create", "ffmp_bind", "ffmp_destroy",
     "ffmp_reset", "ffmp_step", "ffmp_rollout", "ffmp_step_host", "ffmp_step_host_async", "ffmp_step_host_wait", "ffmp_obs_slot", "ffmp_join", "ffmp_error_word", "ffmp_timing", "ffmp_launch_count", "ffmp_debug_trace", "ffmp_learner_input", "ffmp_scan", "ffmp_op_scan",
+    "ffmp_feed_create", "ffmp_feed_handle", "ffmp_feed_connect", "ffmp_feed_info", "ffmp_feed_push", "ffmp_feed_wait", "ffmp_feed_release", "ffmp_feed_error", "ffmp_feed_destroy",
     "ffmp_op_scenarios", "ffmp_op_flow_field_workspace", "ffmp_op_flow_field", "ffmp_op_rewarder", "ffmp_op_rewarder2", "ffmp_op_reward_calculator",
 ]
 
@@ -78,6 +79,15 @@ def lib() -> C.CDLL:
     L.ffmp_learner_input.argtypes = [vp, vp, i32, C.c_float, vp]
     L.ffmp_scan.argtypes = [vp, i32, C.c_float, vp, vp, vp]
     L.ffmp_op_scan.argtypes = [i32, i32, i32, vp, i32, vp, i32, C.c_float, vp, vp, vp]
+    L.ffmp_feed_create.argtypes = [i32, i32, i32, C.c_size_t, C.POINTER(vp)]
+    L.ffmp_feed_handle.argtypes = [vp, vp]
+    L.ffmp_feed_connect.argtypes = [vp, i32, vp]
+    L.ffmp_feed_info.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(u32)]
+    L.ffmp_feed_push.argtypes = [vp, vp, u32, C.c_double, vp]
+    L.ffmp_feed_wait.argtypes = [vp, u32, C.c_double, C.POINTER(vp), vp]
+    L.ffmp_feed_release.argtypes = [vp, u32, vp]
+    L.ffmp_feed_error.argtypes = [vp, C.POINTER(u32), vp]
+    L.ffmp_feed_destroy.argtypes = [vp]
     L.ffmp_error_word.argtypes = [vp, C.POINTER(u32), vp]
     L.ffmp_op_scenarios.argtypes = [i32, i32, i32, u32, i32, i32, u64, vp, vp, vp, vp, vp]
     L.ffmp_op_flow_field_workspace.restype = C.c_size_t

@@ -107,3 +107,110 @@ class EpisodeStats:
         n = max(float(t[2]), 1.0)
         return {"episodes": int(t[2]), "mean_return": float(t[0]) / n, "mean_length": float(t[1]) / n,
                 "reach_rate": float(t[3]) / n, "collision_rate": float(t[4]) / n}
+
+
+class _DevicePointer:
+    """A library-owned device allocation as a __cuda_array_interface__ object (torch.as_tensor wraps it without a copy)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+class LearnerFeed:
+    """The learner feed as one kernel over NVLink peer memory (csrc/feed.cu, include/ffmp_b200.h) instead of
+    pack_transitions + all_gather_into_tensor: every rank's push kernel stores its packed transition block straight into
+    the gather buffers of the destination ranks, which map each other's buffers through CUDA IPC.  Only the 64-byte IPC
+    handles travel through torch.distributed, once, at construction.
+
+        feed = LearnerFeed(env)                 # on every rank (collective: exchanges the handles)
+        feed.push()                             # after env.step(): this rank's block -> every destination
+        obs, reward, done = feed.wait()         # zero-copy views [world, N, ...] into the gather buffer (stream ordered)
+        ... consume ...
+        feed.release()                          # hand the buffer back to the producers
+
+    dest = None pushes to every rank (all-gather semantics); dest = [0] feeds a single learner rank (gather).  A rank that is
+    not a destination skips wait() / release()."""
+
+    def __init__(self, env, dest=None, group=None, timeout_s=10.0):
+        import ctypes as C
+        from . import native
+        self._C, self._native, self._L = C, native, native.lib()
+        self.env, self.group, self.timeout_s = env, group, float(timeout_s)
+        on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if on else 1
+        self.rank = dist.get_rank(group) if on else 0
+        self.N, self.W = env.num_envs, env.config.window
+        self.block = transition_nbytes(self.N, self.W)
+        self.dest = list(range(self.world)) if dest is None else sorted(int(d) for d in dest)
+        self.dest_mask = sum(1 << d for d in self.dest)
+        self.src_mask = (1 << self.world) - 1
+        self._f = C.c_void_p()
+        native.check(self._L.ffmp_feed_create(env.device.index, self.world, self.rank, self.block, C.byref(self._f)), "ffmp_feed_create")
+        handle = (C.c_uint8 * 64)()
+        native.check(self._L.ffmp_feed_handle(self._f, handle), "ffmp_feed_handle")
+        handles = [bytes(handle)]
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+        for r, hb in enumerate(handles):
+            if r != self.rank:
+                buf = (C.c_uint8 * 64).from_buffer_copy(hb)
+                native.check(self._L.ffmp_feed_connect(self._f, r, buf), f"ffmp_feed_connect({r})")
+        base, slot, bufstride = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        native.check(self._L.ffmp_feed_info(self._f, C.byref(base), C.byref(slot), C.byref(bufstride), None), "ffmp_feed_info")
+        self.slot_stride, self.buffer_stride = slot.value, bufstride.value
+        with torch.cuda.device(env.device):
+            self._mem = torch.as_tensor(_DevicePointer(base.value, 2 * bufstride.value), device=env.device)
+        self._views = [self._make_views(b) for b in range(2)]
+        self.seq = 0
+        if self.world > 1:
+            dist.barrier(group=group)        # every rank has mapped every buffer before the first push
+
+    def _make_views(self, b):
+        n, w, world, ss = self.N, self.W, self.world, self.slot_stride
+        ww = w * w
+        raw = self._mem
+        base = b * self.buffer_stride                      # as_strided offsets are absolute in the storage
+        maps = raw.as_strided((world, n, 2, w, w), (ss, 2 * ww, ww, w, 1), base)
+        off = base + n * 2 * ww
+
+        def f32(offset, cols):
+            v = raw.as_strided((world, n * cols * 4), (ss, 1), offset)
+            return v.view(torch.float32).view(world, n, cols) if cols > 1 else v.view(torch.float32)
+        rel_goal, velocity, reward = f32(off, 2), f32(off + 8 * n, 2), f32(off + 16 * n, 1)
+        done = raw.as_strided((world, n), (ss, 1), off + 20 * n)
+        return {"local_map": maps, "relative_goal": rel_goal, "velocity": velocity}, reward, done
+
+    def _stream(self):
+        return self._C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
+
+    def push(self):
+        self._native.check(self._L.ffmp_feed_push(self.env._h, self._f, self.dest_mask, self.timeout_s, self._stream()), "ffmp_feed_push")
+        self.seq += 1
+
+    def wait(self):
+        """(obs, reward, done) of the global batch as views [world, N, ...] (done: uint8); valid until release()."""
+        buf = self._C.c_void_p()
+        self._native.check(self._L.ffmp_feed_wait(self._f, self.src_mask, self.timeout_s, self._C.byref(buf), self._stream()), "ffmp_feed_wait")
+        return self._views[self.seq & 1]
+
+    def release(self):
+        self._native.check(self._L.ffmp_feed_release(self._f, self.src_mask, self._stream()), "ffmp_feed_release")
+
+    def error_word(self) -> int:
+        w = self._C.c_uint32()
+        self._native.check(self._L.ffmp_feed_error(self._f, self._C.byref(w), self._stream()), "ffmp_feed_error")
+        return w.value
+
+    def close(self):
+        if self._f is not None and self._f.value:
+            self._mem = None
+            self._views = None
+            self._L.ffmp_feed_destroy(self._f)
+            self._f = self._C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

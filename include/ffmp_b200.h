@@ -169,6 +169,31 @@ int ffmp_join(ffmp_handle *h, void *stream);
 /* Device error word accumulated by the kernels (bit0: action id out of range). Synchronises `stream`. */
 int ffmp_error_word(ffmp_handle *h, uint32_t *out, void *stream);
 
+/* ---- learner feed over NVLink peer memory (replaces pack + NCCL all-gather of the transition block) ----
+ * One ffmp_feed per rank (one process per GPU).  The library allocates a gather buffer [2][world][slot] on `device`; the
+ * ranks exchange its 64-byte CUDA IPC handle out of band (torch.distributed all_gather_object) and map each other's buffer
+ * with ffmp_feed_connect.  Every step, on every rank (SPMD, same order):
+ *   ffmp_feed_push(env, feed, dest_mask, ...)   one kernel reads the rank's transition block where the step left it (two
+ *       newest ring frames, relative_goal, velocity, reward, done) and stores it in the packed layout
+ *       [maps u8 N*2*W*W | rel_goal f32 N*2 | velocity f32 N*2 | reward f32 N | done u8 N] into slot `rank` of every
+ *       destination rank's buffer (bit r of dest_mask) over NVLink, then publishes the push sequence number there;
+ *   ffmp_feed_wait(feed, src_mask, ...)         stream-ordered (a spin kernel, no host sync) until the listed sources'
+ *       blocks of the current sequence number have arrived; *buffer_dev = [world][slot_stride] of this sequence number;
+ *   ffmp_feed_release(feed, src_mask, ...)      after the consumer's reads (stream order): returns the buffer to the
+ *       producers.  Two buffers alternate, so a producer is at most one step ahead of its slowest consumer.
+ * block_bytes must equal N * (2 W^2 + 21).  A wait that exceeds timeout_s sets bit 1 of the feed's error word.        */
+typedef struct ffmp_feed ffmp_feed;
+#define FFMP_IPC_HANDLE_BYTES 64
+int ffmp_feed_create(int32_t device, int32_t world, int32_t rank, size_t block_bytes, ffmp_feed **out);
+int ffmp_feed_handle(ffmp_feed *f, uint8_t *handle_out);
+int ffmp_feed_connect(ffmp_feed *f, int32_t peer_rank, const uint8_t *handle);
+int ffmp_feed_info(const ffmp_feed *f, void **base_dev, size_t *slot_stride, size_t *buffer_stride, uint32_t *seq);
+int ffmp_feed_push(ffmp_handle *h, ffmp_feed *f, uint32_t dest_mask, double timeout_s, void *stream);
+int ffmp_feed_wait(ffmp_feed *f, uint32_t src_mask, double timeout_s, void **buffer_dev, void *stream);
+int ffmp_feed_release(ffmp_feed *f, uint32_t src_mask, void *stream);
+int ffmp_feed_error(ffmp_feed *f, uint32_t *out, void *stream);
+int ffmp_feed_destroy(ffmp_feed *f);
+
 /* ---- stateless operators (what the reference's external ROS nodes computed) ------------------- */
 
 /* Scenario generator (SPEC.md §3): for item n, env id env_gid_dev[n] (u32) and episode episode_dev[n]

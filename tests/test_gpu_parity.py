@@ -544,3 +544,48 @@ def test_scan_env_rollout_and_rewarder2(ffmp, cuda_device):
             reward, done, flags = ffmp.ops.rewarder2(s64, env.rel_goal, torch.ones(N, dtype=torch.uint8, device=cuda_device), d_first)
             assert np.array_equal(t2n(flags) & 1, eh), t
     env.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# learner feed through the peer-memory push kernel (world size 1 here: the destination is the rank's own buffer; the
+# cross-GPU path is exercised by tools/feed_bench.py on a multi-GPU box)
+# ---------------------------------------------------------------------------------------------------
+def test_learner_feed_push_matches_pack_transitions(ffmp, cuda_device):
+    from flow_field_based_motion_planner_b200 import sharding
+    N, W = 48, 32
+    env = ffmp.FFMPVectorEnv(N, seed=5, grid=64, window=W, ring=4, max_steps=15)
+    env.reset()
+    feed = sharding.LearnerFeed(env)
+    assert feed.world == 1 and feed.block == sharding.transition_nbytes(N, W)
+    rng = np.random.default_rng(1)
+    for t in range(40):                       # ring wraps, auto-resets, both buffers and the credit path (seq > 2)
+        obs, reward, done, _ = env.step(torch.as_tensor(rng.integers(0, 28, N), device=cuda_device))
+        feed.push()
+        g_obs, g_reward, g_done = feed.wait()
+        expect = sharding.pack_transitions(obs, reward, done)
+        e_obs, e_reward, e_done = sharding.unpack_transitions(expect, N, W)
+        assert torch.equal(g_obs["local_map"][0], e_obs["local_map"]), t
+        assert torch.equal(g_obs["relative_goal"][0].view(torch.int32), e_obs["relative_goal"].view(torch.int32)), t
+        assert torch.equal(g_obs["velocity"][0].view(torch.int32), e_obs["velocity"].view(torch.int32)), t
+        assert torch.equal(g_reward[0].view(torch.int32), e_reward.view(torch.int32)), t
+        assert torch.equal(g_done[0] != 0, e_done), t
+        # the raw slot is the packed block, byte for byte
+        raw = feed._mem[(feed.seq & 1) * feed.buffer_stride:][:feed.block]
+        assert torch.equal(raw, expect), t
+        feed.release()
+    assert feed.error_word() == 0
+    feed.close()
+    env.close()
+
+
+def test_learner_feed_credit_timeout_sets_error_bit(ffmp, cuda_device):
+    """A producer that is two pushes ahead of an unreleased buffer waits for the credit; the bounded spin gives up and flags it."""
+    from flow_field_based_motion_planner_b200 import sharding
+    env = ffmp.FFMPVectorEnv(8, seed=5, grid=64, window=32)
+    env.reset()
+    feed = sharding.LearnerFeed(env, timeout_s=0.05)
+    for _ in range(3):                        # the third push needs buffer 1 back, nobody released it
+        feed.push()
+    assert feed.error_word() & 2
+    feed.close()
+    env.close()
