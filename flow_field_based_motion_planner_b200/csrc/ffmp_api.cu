@@ -615,6 +615,13 @@ int ffmp_obs_slot(const ffmp_handle *h, int32_t *newest_slot) {
     return FFMP_OK;
 }
 
+int ffmp_set_obs_slot(ffmp_handle *h, int32_t newest_slot) {
+    if (!h) return fail(FFMP_ERR_ARG, "handle is null");
+    if (newest_slot < 1 || newest_slot > (h->cfg.ring > 2 ? h->cfg.ring - 1 : 1)) return fail(FFMP_ERR_ARG, "newest_slot out of range");
+    h->p = newest_slot;
+    return FFMP_OK;
+}
+
 int ffmp_learner_input(ffmp_handle *h, void *out_dev, int32_t dtype, float scale, void *stream) {
     if (!h || !out_dev) return fail(FFMP_ERR_ARG, "null argument");
     if (!h->ready) return fail(FFMP_ERR_STATE, "ffmp_reset must be called before ffmp_learner_input");

@@ -145,7 +145,8 @@ class FFMPVectorEnv:
         return reward, rel_goal, velocity, done, flags
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        # the raw handle of torch's current stream on the env's device (torch.cuda.current_stream() builds a Stream object: ~1 us)
+        return C.c_void_p(torch._C._cuda_getCurrentRawStream(self.device.index))
 
     def _obs(self):
         p = C.c_int32()
@@ -221,11 +222,13 @@ class FFMPVectorEnv:
     def step_async(self, actions_host):
         """gym.vector's step_async with host buffers: queue one step on actions int64[N] in (pinned) host memory and
         return at once; the buffer must stay untouched until step_wait() returns."""
-        self._host_buffers()
+        if self._host is None:
+            self._host_buffers()
         a = actions_host
-        assert a.dtype == torch.int64 and a.device.type == "cpu" and a.numel() == self.num_envs and a.is_contiguous()
+        if not (a.dtype == torch.int64 and a.device.type == "cpu" and a.numel() == self.num_envs and a.is_contiguous()):
+            raise ValueError("step_async expects a contiguous int64 CPU tensor with one action id per env")
         # the library switches to its own device (DeviceGuard): no torch device context here
-        rc = self._L.ffmp_step_host_async(self._h, C.c_void_p(a.data_ptr()), *self._host_ptrs, self._stream())
+        rc = self._L.ffmp_step_host_async(self._h, a.data_ptr(), *self._host_ptrs, self._stream())
         if rc:
             native.check(rc, "ffmp_step_host_async")
         self._pending_actions = a        # keeps the buffer alive while the kernel reads it in place
@@ -344,6 +347,54 @@ class FFMPVectorEnv:
         """Direction codes 0..7, 8 = none (SPEC.md §5 decoding of the flow image)."""
         img = self.flow_image()
         return torch.where(img == 255, torch.full_like(img, 8), img // 28)
+
+    # ---- checkpoint / resume of the env (SURVEY.md §5: env checkpoint = the state tensors + RNG counters) -----------
+    _STATE_TENSORS = ("state", "scen", "flow", "cost", "frames", "reward", "rel_goal", "velocity", "done", "flags",
+                      "term_rel_goal", "term_velocity", "fin_return", "fin_length")
+
+    def state_dict(self, planes=True):
+        """Everything a later load_state_dict needs to continue bit-identically: the per-env state records, the resident
+        scenario slots (every random draw is keyed by (seed, global env id, episode), so there is no RNG state beyond the
+        episode counters), the frame ring and the library's step counter.  planes=False leaves out the flow / cost planes
+        (S*N*G*G*5 bytes); load_state_dict then regenerates them from the scenario keys."""
+        self.join()
+        torch.cuda.synchronize(self.device)
+        p = C.c_int32()
+        native.check(self._L.ffmp_obs_slot(self._h, C.byref(p)), "ffmp_obs_slot")
+        names = [n for n in self._STATE_TENSORS if planes or n not in ("flow", "cost")]
+        return {"config": dict(self.config.__dict__), "newest_slot": p.value, "planes": bool(planes),
+                "tensors": {n: getattr(self, n).detach().cpu().clone() for n in names}}
+
+    def load_state_dict(self, sd):
+        """Restore a state_dict taken from an env of the same configuration (device may differ)."""
+        want = {k: v for k, v in sd["config"].items() if k != "device"}
+        have = {k: v for k, v in self.config.__dict__.items() if k != "device"}
+        if want != have:
+            raise ValueError(f"checkpoint config {want} does not match this env {have}")
+        self.reset()                                   # arms the library (lists, counters) and regenerates every slot
+        self.join()
+        for n, t in sd["tensors"].items():
+            getattr(self, n).copy_(t.to(self.device))
+        if not sd.get("planes", True):
+            self._regenerate_planes()
+        native.check(self._L.ffmp_set_obs_slot(self._h, int(sd["newest_slot"])), "ffmp_set_obs_slot")
+        torch.cuda.synchronize(self.device)
+        return self
+
+    def _regenerate_planes(self):
+        """flow / cost planes of every resident slot from the scenario records' episode keys (checkpoint without planes)."""
+        from . import ops
+        S, N, G = self.config.slots, self.num_envs, self.config.grid
+        ep = self.episode().to(torch.int64)                                       # current episode k of every env
+        gids = torch.arange(N, device=self.device) + self.config.env_id_base
+        for s in range(S):
+            # slot s holds the episode e >= k with e % S == s (the library regenerates a consumed slot for episode k + S - 1)
+            e = ep + ((s - ep) % S)
+            occ, scen = ops.generate_scenarios(gids, e, G, p_occ=self.config.p_occ, goal_mode=self.config.goal_mode,
+                                               block_shift=self.config.block_shift, seed=self.config.seed)
+            cost, flow = ops.flow_field(occ, scen[:, 5:7].contiguous())
+            self.flow[s].copy_(flow)
+            self.cost[s].copy_(cost)
 
     def close(self):
         h = getattr(self, "_h", None)

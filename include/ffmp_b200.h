@@ -153,6 +153,10 @@ int ffmp_debug_trace(ffmp_handle *h, uint64_t *out_host, void *stream);
 /* Index of the newest frame slot p (1 <= p <= K-1): the observation is frames[:, p-1 : p+1]. */
 int ffmp_obs_slot(const ffmp_handle *h, int32_t *newest_slot);
 
+/* Resume support: set the newest frame slot after the caller restored the bound buffers from a checkpoint (a full
+ * ffmp_reset must have run on this handle first).                                                                 */
+int ffmp_set_obs_slot(ffmp_handle *h, int32_t newest_slot);
+
 /* The current observation as the learner's input tensor (replaces make_temporal_maps + `.float()` + `.to(device)`,
  * src/train.py:474-486, 539-545): out = f32 (dtype 0) or bf16 (dtype 1) [N][2][W][W], oldest frame first, pixel value
  * times `scale` (1.0 = the reference's plain float cast).  out_dev: caller-allocated device memory, 16-byte aligned.   */

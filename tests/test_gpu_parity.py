@@ -589,3 +589,29 @@ def test_learner_feed_credit_timeout_sets_error_bit(ffmp, cuda_device):
     assert feed.error_word() & 2
     feed.close()
     env.close()
+
+
+@pytest.mark.parametrize("planes", [True, False])
+def test_env_checkpoint_resume_is_bit_identical(ffmp, cuda_device, planes):
+    """state_dict() in the middle of a rollout, then the same actions on (a) the original env and (b) a fresh env that
+    loaded the checkpoint: identical results step by step, with and without the flow / cost planes in the checkpoint."""
+    N = 32
+    kw = dict(seed=11, grid=64, window=32, ring=4, slots=3, max_steps=12)
+    env = ffmp.FFMPVectorEnv(N, **kw)
+    env.reset()
+    rng = np.random.default_rng(2)
+    for _ in range(37):
+        env.step(torch.as_tensor(rng.integers(0, 28, N), device=cuda_device))
+    sd = env.state_dict(planes=planes)
+    other = ffmp.FFMPVectorEnv(N, **kw)
+    other.load_state_dict(sd)
+    for t in range(60):
+        a = torch.as_tensor(rng.integers(0, 28, N), device=cuda_device)
+        o1, r1, d1, i1 = env.step(a)
+        o2, r2, d2, i2 = other.step(a)
+        assert torch.equal(r1.view(torch.int32), r2.view(torch.int32)) and torch.equal(d1, d2), t
+        assert torch.equal(o1["local_map"], o2["local_map"]), t
+        assert torch.equal(o1["relative_goal"].view(torch.int32), o2["relative_goal"].view(torch.int32)), t
+        assert torch.equal(i1["flags"], i2["flags"]), t
+    assert torch.equal(env.cost_field(), other.cost_field()) and torch.equal(env.flow_image(), other.flow_image())
+    env.close(); other.close()

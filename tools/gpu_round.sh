@@ -9,6 +9,9 @@ timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; ech
 timeout 300 python bench.py --impl reference --steps 100 --warmup 5 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
 timeout 300 python tools/kbench.py > gpurun_out/kbench.json 2> gpurun_out/kbench.err; echo "kbench rc=$?"
 timeout 400 python tools/sweep.py > gpurun_out/sweep.txt 2>&1; echo "sweep rc=$?"
+timeout 200 python tools/e2e_ab.py 4096 3000 > gpurun_out/e2e_ab.txt 2>&1; echo "e2e_ab rc=$?"
+FFMP_HOST_IO_STATS=1 timeout 100 python tools/e2e_ab.py child 4096 3000 > gpurun_out/e2e_stats.txt 2>&1
+timeout 120 python tools/feed_bench.py --steps 100 > gpurun_out/feed_bench_1gpu.txt 2>&1; echo "feed rc=$?"
 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/plain_bench.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_bench.csv \
     python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu launches rc=$?"
