@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
                 }
         }
         // one BFS level; KSEL = 0 / 1: the Gray plane of this level is G0 / G1 (registers), 2: plane ctz(L) >= 2
-        auto level = [&](auto ksel, uint32_t L) -> uint32_t {
+        auto level = [&](auto ksel, uint32_t L) {
             constexpr int KSEL = decltype(ksel)::value;
             if constexpr (KSEL == 0) {
 #pragma unroll
@@ -279,27 +279,28 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
                     const uint32_t dn = r == RPL - 1 ? dnF[w] : F[r + 1][w];
                     Nw[r][w] = (from_lo<WPR, IL>(F[r], w) | from_hi<WPR, IL>(F[r], w) | up | dn) & A[r][w];
                 }
-            uint32_t any = 0;
 #pragma unroll
             for (int r = 0; r < RPL; ++r)
 #pragma unroll
                 for (int w = 0; w < WPR; ++w) {
                     A[r][w] = sub_on_fma(A[r][w], Nw[r][w], neg1);
                     F[r][w] = Nw[r][w];
-                    if constexpr (KSEL >= 2) any |= Nw[r][w];
                 }
-            return any;
         };
         // Two levels of code (odd level: Gray plane 0, static; even level: plane ctz(L) >= 1, dynamic) executed twice per
         // convergence vote: half the instruction footprint of a four-level body (the loop showed 13 % no-instruction stalls).
         uint32_t L = 1;
         for (;; L += 4) {
-            uint32_t any = 0;
 #pragma unroll 1
             for (uint32_t h = 0; h < 4; h += 2) {
                 level(Int<0>{}, L + h);
-                any = level(Int<3>{}, L + h + 1);
+                level(Int<3>{}, L + h + 1);
             }
+            uint32_t any = 0;                           // the frontier of the fourth level, OR-ed once per vote
+#pragma unroll
+            for (int r = 0; r < RPL; ++r)
+#pragma unroll
+                for (int w = 0; w < WPR; ++w) any |= F[r][w];
             if (!__any_sync(FULL, any != 0)) break;     // an empty frontier stays empty: test every fourth level
         }
 #pragma unroll
@@ -506,7 +507,9 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
                     if constexpr (IL) {
                         // interleaved: byte j of transpose8(word w, byte group b) is the cost of column 4(8b+j)+w, so a 4x4 byte
                         // transpose across the four words yields the 32 consecutive columns 32b .. 32b+31 (chunks 2b, 2b+1)
-                        uint32_t tl[4][4], th[4][4];
+                        uint32_t tl[4][4], th[4][4], Vr[WPR];
+                        const int Rr = lane * RPL + r;
+                        Row<WPR>::ld(&pl[pidx(PVIS, r, lane)], Vr);
 #pragma unroll
                         for (int w = 0; w < 4; ++w) {
                             bytes4x4(Bk[0][w], Bk[1][w], Bk[2][w], Bk[3][w], tl[w]);
@@ -522,10 +525,25 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
                             }
                             bytes4x4(lo[0], lo[1], lo[2], lo[3], x);
                             bytes4x4(hb[0], hb[1], hb[2], hb[3], y);
-                            const int s0 = SWZ ? ((2 * b) ^ ((lane / (8 / CH)) % CH)) : 2 * b;
-                            const int s1 = SWZ ? ((2 * b + 1) ^ ((lane / (8 / CH)) % CH)) : 2 * b + 1;
-                            *reinterpret_cast<uint4 *>(phys(lane * P + 16 * s0)) = make_uint4(x[0], x[1], x[2], x[3]);
-                            *reinterpret_cast<uint4 *>(phys(lane * P + 16 * s1)) = make_uint4(y[0], y[1], y[2], y[3]);
+                            // x[j] / y[j] = the cost bytes of columns 4n .. 4n+3 with n = 8b + j / 8b + 4 + j; their visited bits are
+                            // bit n of the row's four interleaved words.  The lane widens and stores its own row: the 32 16-byte
+                            // stores of a row fill its four 128-byte lines (no staging, no second pass over shared memory).
+                            if (Rr < G) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const int n = 8 * b + j;
+                                    if (4 * n < G) {
+                                        const uint32_t b4 = j < 4 ? x[j & 3] : y[j & 3];
+                                        const uint32_t bit = 1u << n;
+                                        int4 c;
+                                        c.x = (Vr[0] & bit) ? static_cast<int>(__byte_perm(b4, 0u, 0x4440)) : COST_INF;
+                                        c.y = (Vr[1] & bit) ? static_cast<int>(__byte_perm(b4, 0u, 0x4441)) : COST_INF;
+                                        c.z = (Vr[2] & bit) ? static_cast<int>(__byte_perm(b4, 0u, 0x4442)) : COST_INF;
+                                        c.w = (Vr[3] & bit) ? static_cast<int>(__byte_perm(b4, 0u, 0x4443)) : COST_INF;
+                                        *reinterpret_cast<int4 *>(cost + static_cast<size_t>(Rr) * G + 4 * n) = c;
+                                    }
+                                }
+                            }
                         }
                     } else {
 #pragma unroll
@@ -551,7 +569,7 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
                     }
                     __syncwarp();
                     const int col = 4 * lane;
-                    if (col < G) {
+                    if (!IL && col < G) {
 #pragma unroll 4
                         for (int i = 0; i < 32; ++i) {
                             const int R = i * RPL + r;
