@@ -199,8 +199,15 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
     const int l = static_cast<int>(h->step_index % static_cast<uint64_t>(h->nlist));
     if (h->regen_pending[l]) {
         // the regeneration that last used list `l` (S-1 ticks ago) must be complete: it re-armed the
-        // list and filled the scenario slot an env may switch to in this tick
-        CK(cudaStreamWaitEvent(st, h->ev_regen[l], 0));
+        // list and filled the scenario slot an env may switch to in this tick.  If the host already sees it complete
+        // (the usual case when the caller synchronises every step) no device-side wait is queued in front of the tick.
+        const cudaError_t q = cudaEventQuery(h->ev_regen[l]);
+        if (q == cudaErrorNotReady) {
+            cudaGetLastError();   // "not ready" is a status, not a failure: keep it out of the launchers' error checks
+            CK(cudaStreamWaitEvent(st, h->ev_regen[l], 0));
+        } else if (q != cudaSuccess) {
+            return fail(FFMP_ERR_CUDA, "cudaEventQuery(regeneration)", q);
+        }
         h->regen_pending[l] = false;
     }
     ffmp::StepArgs a = step_args(h);
@@ -533,6 +540,7 @@ int ffmp_step_host_wait(ffmp_handle *h) {
         if ((spins & 0x3FFF) == 0) {
             DeviceGuard guard(h->cfg.device);
             const cudaError_t q = cudaStreamQuery(h->wait_stream);
+            if (q == cudaErrorNotReady) cudaGetLastError();
             if (q == cudaSuccess) {
                 if (*h->flag_host == want) break;
                 return fail(FFMP_ERR_CUDA, "the step finished without publishing its completion word");

@@ -35,9 +35,11 @@ __global__ void __launch_bounds__(1024) host_export_kernel(HostExportArgs a) {
         uint32_t *d = reinterpret_cast<uint32_t *>(dst + a.n16);
         d[threadIdx.x] = __ldcg(s + threadIdx.x);
     }
-    __threadfence_system();
+    // The CTA barrier orders every thread's stores before thread 0's system-scope fence (cumulativity), so ONE fence
+    // publishes the whole block; 32 warps fencing at system scope one after the other cost microseconds.
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         if (a.stamps) {   // diagnostics (FFMP_HOST_IO_STATS=1): resident / grid dependency released / block written
             unsigned long long g2;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g2));
