@@ -508,14 +508,16 @@ def test_scan_operator_bit_exact(ffmp, cuda_device, G, beams, rmax, flow_mode):
     assert (scan > 0).any()
 
 
-def test_scan_generic_kernel_matches_windowed(ffmp, cuda_device, monkeypatch):
-    """FFMP_SCAN_GENERIC=1 forces the global-load kernel (used for range_max beyond the shared-memory window)."""
+def test_scan_kernel_variants_agree(ffmp, cuda_device, monkeypatch):
+    """Default = shared-memory window kernel; FFMP_SCAN_GENERIC=1 = global-load kernel (used for range_max beyond the window)."""
     env = ffmp.FFMPVectorEnv(16, seed=2, grid=128, window=100)
     env.reset()
-    a, ha = env.scan(360, 3.5)
-    monkeypatch.setenv("FFMP_SCAN_GENERIC", "1")
-    b, hb = env.scan(360, 3.5)
-    assert torch.equal(a.view(torch.int32), b.view(torch.int32)) and torch.equal(ha, hb)
+    for beams in (360, 1000):
+        a, ha = env.scan(beams, 3.5)
+        monkeypatch.setenv("FFMP_SCAN_GENERIC", "1")
+        c, hc = env.scan(beams, 3.5)
+        monkeypatch.delenv("FFMP_SCAN_GENERIC")
+        assert torch.equal(a.view(torch.int32), c.view(torch.int32)) and torch.equal(ha, hc), beams
     env.close()
 
 
