@@ -307,6 +307,20 @@ def run_ours(a):
                                     "achieved_gbs": cells * 6 / (ff_ms * 1e-3) / 1e9,
                                     "frac_of_hbm_peak": cells * 6 / (ff_ms * 1e-3) / 1e9 / peak}
 
+            # ---- LiDAR scan synthesis: 360 beams x 3.5 m per env at the current poses ----
+            sc_out = torch.empty((N, 360), dtype=torch.float32, device=dev)
+            for _ in range(3):
+                env.scan(360, 3.5, out=sc_out)
+            torch.cuda.synchronize()
+            x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x.record()
+            for _ in range(5):
+                env.scan(360, 3.5, out=sc_out)
+            y.record()
+            torch.cuda.synchronize()
+            sc_ms = x.elapsed_time(y) / 5
+            extras["scan"] = {"beams": 360, "range_max_m": 3.5, "ms": sc_ms, "beams_per_s": N * 360 / (sc_ms * 1e-3)}
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         # a bounded sample of the same workload, ~10 s of single-thread CPU work
