@@ -56,7 +56,7 @@ def run_flow(ffmp, dev, occs, goals, want_cost=True):
     return (t2n(cost) if want_cost else None), t2n(flow)
 
 
-@pytest.mark.parametrize("G", [16, 32, 64, 96, 100, 128])
+@pytest.mark.parametrize("G", [16, 32, 64, 96, 100, 112, 124, 128])
 def test_flow_field_special_maps_bit_exact(ffmp, cuda_device, G):
     cases = special_cases(G)
     cost, flow = run_flow(ffmp, cuda_device, [c[1] for c in cases], [c[2] for c in cases])
@@ -240,6 +240,13 @@ def test_rollout_ring_and_slot_variants(ffmp, ring, slots):
 def test_rollout_dense_obstacles_short_episodes(ffmp):
     """p=0.3 per-cell noise: episodes of a few steps, so nearly every step regenerates slots."""
     rollout_parity(ffmp, 32, 200, seed=9, grid=128, window=100, p_occ=0.3, block_shift=0, check_every=50)
+
+
+@pytest.mark.parametrize("grid,bs,p", [(112, 1, 0.05), (124, 2, 0.15), (128, 5, 0.2), (104, 7, 0.1)])
+def test_rollout_interleaved_generator_block_sizes(ffmp, grid, bs, p):
+    """Grids in (96, 128] use the column-interleaved layout; its in-kernel scenario generator has separate code for
+    block_shift < 2, 2..6 and >= 7, and the row stores differ for G % 16 != 0."""
+    rollout_parity(ffmp, 24, 120, seed=13, grid=grid, window=32, p_occ=p, block_shift=bs, max_steps=15, check_every=40)
 
 
 def test_sharded_env_ids(ffmp):
