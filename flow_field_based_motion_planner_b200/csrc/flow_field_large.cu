@@ -59,6 +59,13 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
     uint32_t *const fb0 = pls + NPSL * PLANE_WORDS;
     uint32_t *const fb1 = fb0 + FBUF_WORDS;
     uint32_t *const pv = fb0, *const pf = fb1;
+    // activity masks of the published frontier rows (double buffered like the rows, P + 2 entries each incl. the ghost rows):
+    //   bits 0..3  chunk q (words 4q..4q+3) of the row is non-zero
+    //   bits 4..7  bit 31 of the chunk's last word is set  (the row's chunk q+1 sees it as its west neighbour)
+    //   bits 8..11 bit 0 of the chunk's first word is set  (the row's chunk q-1 sees it as its east neighbour)
+    uint16_t *const am0 = reinterpret_cast<uint16_t *>(fb1 + FBUF_WORDS);
+    uint16_t *const am1 = am0 + (P + 2);
+    constexpr uint32_t NZ_MASK = (1u << NQ) - 1u;
 
     const int tid = threadIdx.x;
     const int row = tid;
@@ -145,9 +152,17 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
             if (tid < 2) {            // ghost rows -1 and P of both frontier buffers
                 sm_st(fb0, P + 2, tid * (P + 1), z);
                 sm_st(fb1, P + 2, tid * (P + 1), z);
+                am0[tid * (P + 1)] = 0; am1[tid * (P + 1)] = 0;
             }
         }
         sm_st(fb0, P + 2, row + 1, F);
+        uint32_t m_own = 0;           // activity mask of this thread's frontier row (see above)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const uint32_t nz = F[4 * q] | F[4 * q + 1] | F[4 * q + 2] | F[4 * q + 3];
+            m_own |= (nz != 0 ? 1u : 0u) << q | (F[4 * q + 3] >> 31) << (4 + q) | (F[4 * q] & 1u) << (8 + q);
+        }
+        am0[row + 1] = static_cast<uint16_t>(m_own);
         __syncthreads();
 
         // ---- 2. bit-parallel wavefront -----------------------------------------------------------------
@@ -156,6 +171,7 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
         // frontier row is published into the other buffer, and one __syncthreads_or both orders the exchange and tests
         // convergence.
         uint32_t *fcur = fb0, *fnext = fb1;
+        uint16_t *acur = am0, *anext = am1;
         uint32_t L = 1;
         for (;; ++L) {
             // Gray bit-plane update: cells with cost >= L flip Gray bit ctz(L)
@@ -184,24 +200,44 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
                 }
                 Row<WPR>::st(p, v);
             }
-            uint32_t up[WPR], dn[WPR];
-            sm_ld(fcur, P + 2, row, up);          // buffer row r+1 holds grid row r: row - 1 -> index row
-            sm_ld(fcur, P + 2, row + 2, dn);
-            uint32_t any = 0, f_prev = 0;
+            // Which chunks can receive new cells at this level?  Those that hold frontier cells in this row or in the rows above /
+            // below, plus the horizontal neighbours of an edge bit.  OR-ed over the warp (one REDUX) the answer is warp-uniform:
+            // a skipped chunk costs nothing, and its frontier words are zero before and after (they were part of the test).
+            uint32_t act = (m_own | acur[row] | acur[row + 2]) & NZ_MASK;
+            act |= (((m_own >> 4) & NZ_MASK) << 1) | (((m_own >> 8) & NZ_MASK) >> 1);
+            const uint32_t wact = __reduce_or_sync(FULL, act & NZ_MASK);
+            uint32_t any = 0, f_prev = 0, m_new = 0;
 #pragma unroll
-            for (int w = 0; w < WPR; ++w) {
-                const uint32_t f_cur = F[w], f_next = w + 1 < WPR ? F[w + 1] : 0u;
-                const uint32_t lo = w > 0 ? __funnelshift_l(f_prev, f_cur, 1) : f_cur << 1;
-                const uint32_t hv = w + 1 < WPR ? __funnelshift_r(f_cur, f_next, 1) : f_cur >> 1;
-                const uint32_t n = (lo | hv | up[w] | dn[w]) & A[w];
-                any |= n;
-                A[w] = sub_on_fma(A[w], n, neg1);
-                F[w] = n;
-                f_prev = f_cur;
+            for (int q = 0; q < NQ; ++q) {
+                if (wact & (1u << q)) {
+                    const uint4 u4 = *reinterpret_cast<const uint4 *>(fcur + (q * (P + 2) + row) * 4);        // grid row - 1
+                    const uint4 d4 = *reinterpret_cast<const uint4 *>(fcur + (q * (P + 2) + row + 2) * 4);    // grid row + 1
+                    const uint32_t up[4] = {u4.x, u4.y, u4.z, u4.w}, dn[4] = {d4.x, d4.y, d4.z, d4.w};
+                    uint32_t nz = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int w = 4 * q + j;
+                        const uint32_t f_cur = F[w], f_next = w + 1 < WPR ? F[w + 1] : 0u;
+                        const uint32_t lo = w > 0 ? __funnelshift_l(f_prev, f_cur, 1) : f_cur << 1;
+                        const uint32_t hv = w + 1 < WPR ? __funnelshift_r(f_cur, f_next, 1) : f_cur >> 1;
+                        const uint32_t n = (lo | hv | up[j] | dn[j]) & A[w];
+                        nz |= n;
+                        A[w] = sub_on_fma(A[w], n, neg1);
+                        F[w] = n;
+                        f_prev = f_cur;
+                    }
+                    any |= nz;
+                    m_new |= (nz != 0 ? 1u : 0u) << q | (F[4 * q + 3] >> 31) << (4 + q) | (F[4 * q] & 1u) << (8 + q);
+                } else {
+                    f_prev = 0;       // == the (zero) last frontier word of the skipped chunk
+                }
             }
             sm_st(fnext, P + 2, row + 1, F);
+            anext[row + 1] = static_cast<uint16_t>(m_new);
+            m_own = m_new;
             if (!__syncthreads_or(any != 0)) break;
             uint32_t *t = fcur; fcur = fnext; fnext = t;
+            uint16_t *ta = acur; acur = anext; anext = ta;
         }
         const uint32_t Lmax = L - 1;                       // deepest level that reached a cell
         const int kmax = 32 - __clz(Lmax);                  // number of significant cost bits (<= NPMAX)
@@ -373,7 +409,8 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
 int large_wpr(int G) { return G <= 128 ? 4 : G <= 256 ? 8 : 16; }
 size_t large_smem_bytes(int G) {
     const int wpr = large_wpr(G);
-    return (static_cast<size_t>(NPSL) * 32 * wpr * wpr + 2 * static_cast<size_t>(32 * wpr + 2) * wpr) * sizeof(uint32_t);
+    return (static_cast<size_t>(NPSL) * 32 * wpr * wpr + 2 * static_cast<size_t>(32 * wpr + 2) * wpr) * sizeof(uint32_t) +
+           2 * static_cast<size_t>(32 * wpr + 2) * sizeof(uint16_t) + 8;      // + the activity masks of the frontier rows
 }
 
 }  // namespace
