@@ -412,7 +412,7 @@ int ffmp_reset(ffmp_handle *h, const uint8_t *mask_dev, void *stream) {
     for (int s = 0; s < c.slots; ++s) {
         ffmp::FlowArgs fa = flow_args(h);
         fa.count = c.num_envs; fa.episode_const = static_cast<uint32_t>(s);
-        if (c.grid <= 128) { fa.ticket = h->reset_ticket(); fa.work = h->reset_work(); }
+        fa.ticket = h->reset_ticket(); fa.work = h->reset_work();
         CK(ffmp::launch_flow_field(fa, h->ff_grid, st));
         h->launches += 1;
     }
@@ -898,11 +898,9 @@ int ffmp_op_flow_field(int32_t device, int32_t n, int32_t G, const uint8_t *occ_
     a.count = n; a.G = G; a.slot_mode = 0; a.S = 1; a.N = n;
     a.occ = occ_dev; a.goal_cells = goal_cells_dev; a.cost = cost_dev; a.flow = flow_dev;
     if (reinterpret_cast<uintptr_t>(workspace_dev) % 16) return fail(FFMP_ERR_ARG, "workspace must be 16-byte aligned");
-    if (G <= 128) {
-        CK(cudaMemsetAsync(workspace_dev, 0, 16, static_cast<cudaStream_t>(stream)));
-        a.work = static_cast<uint32_t *>(workspace_dev);
-        a.ticket = a.work + 1;
-    }
+    CK(cudaMemsetAsync(workspace_dev, 0, 16, static_cast<cudaStream_t>(stream)));
+    a.work = static_cast<uint32_t *>(workspace_dev);       // dynamic grid hand-out counter + completion ticket
+    a.ticket = a.work + 1;
     a.hi_scratch = static_cast<uint32_t *>(workspace_dev) + 64;
     const int maxg = ffmp::flow_field_max_grid(G);
     CK(ffmp::launch_flow_field(a, n < maxg ? n : maxg, static_cast<cudaStream_t>(stream)));

@@ -23,6 +23,7 @@ constexpr int NPGL = NPMAX - 1 - NPSL;   // planes NPSL+1..17 in the global scra
 constexpr int NSM = NPSL + 2;         // shared-memory planes per CTA: 1..NPSL, visited, free
 
 struct LargeInfo {
+    int item;
     unsigned long long plane;
     int gi, gj;
     uint32_t key;
@@ -90,7 +91,15 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
             *reinterpret_cast<uint4 *>(base + (q * rows + r) * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     };
 
-    for (int item = blockIdx.x; item < count; item += gridDim.x) {
+    // grids are handed out through a device counter (a.work) when there is one: depths differ by 2x between maps, and 512
+    // grids over 148 CTAs would otherwise be four static rounds for every CTA that drew item 444..511
+    for (int item = blockIdx.x;; item += gridDim.x) {
+        if (a.work) {
+            if (tid == 0) info.item = static_cast<int>(atomicAdd(a.work, 1u));
+            __syncthreads();
+            item = info.item;
+        }
+        if (item >= count) break;
         // ---- 0. item parameters ------------------------------------------------------------------------
         if (tid == 0) {
             const uint32_t env = a.env_idx ? a.env_idx[item] : static_cast<uint32_t>(item);
@@ -400,6 +409,7 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
         const uint32_t t = atomicAdd(a.ticket, 1u);
         if (t == gridDim.x - 1) {
             *a.ticket = 0;
+            if (a.work) *a.work = 0;
             if (a.count_reset) *a.count_reset = 0;
             __threadfence();
         }
