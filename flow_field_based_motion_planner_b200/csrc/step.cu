@@ -1223,6 +1223,7 @@ cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t
             }
             if (a.trace) tick_tma_kernel<true, 0><<<a.N, 128, smem, st>>>(*tmap, a);
             else if (a.W == 100) tick_tma_kernel<false, 100><<<a.N, 128, smem, st>>>(*tmap, a);   // the reference's window
+            else if (a.W == 64) tick_tma_kernel<false, 64><<<a.N, 128, smem, st>>>(*tmap, a);     // BASELINE config 2
             else tick_tma_kernel<false, 0><<<a.N, 128, smem, st>>>(*tmap, a);   // the whole tick in one kernel
             return cudaGetLastError();
         }
