@@ -244,11 +244,11 @@ def run_ours(a):
             dt = float(t.item())
         e2e = {"value": world * N * k2 / dt, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step * world,
                "d2h_bytes_per_step": env.d2h_bytes_per_step * world, "steps": k2,
-               "note": "FFMPVectorEnv.step_host every step, host buffers in and out: pinned int64 actions are read in place by the "
-                       "step kernel over PCIe, reward/done/flags/relative_goal/velocity are written into the caller's pinned "
-                       "block by a kernel queued behind the step, and the call returns when its completion word (mapped "
-                       "memory) is set: no copy engine, no stream sync; local_map observations stay on the device for "
-                       "the learner"}
+               "note": "FFMPVectorEnv.step_host every step, host buffers in and out: pinned int64 actions go in with one "
+                       "cudaMemcpyAsync, reward/done/flags/relative_goal/velocity are written into the caller's pinned block by "
+                       "a kernel queued behind the step, and the call returns when its completion word (mapped memory) is set: "
+                       "no device-to-host copy engine, no stream sync; local_map observations stay on the device for the "
+                       "learner"}
 
         # ---- roofline of the dominant kernel of the step (tick_tma_kernel: the whole env step in one launch), timed
         #      live with CUDA events recorded by the library on the launching stream around each launch (ffmp_timing);

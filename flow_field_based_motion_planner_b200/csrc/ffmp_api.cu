@@ -140,7 +140,7 @@ struct ffmp_handle {
     volatile uint32_t *flag_host = nullptr;
     uint32_t *flag_dev = nullptr;
     uint32_t flag_seq = 0;
-    int host_io = 2;                // FFMP_HOST_IO: 0 copy engines + stream sync, 1 mapped results, 2 mapped results + zero-copy actions
+    int host_io = 1;                // FFMP_HOST_IO: 0 copy engines + stream sync, 1 mapped results (default), 2 mapped results + in-place actions
     int wait_mode = 0;              // what ffmp_step_host_wait has to do: 0 nothing, 1 spin on the flag, 2 synchronise wait_stream
     cudaStream_t wait_stream = nullptr;
     // FFMP_HOST_IO_STATS=1: host / device timeline of the host-buffer steps, printed to stderr by ffmp_destroy

@@ -123,11 +123,12 @@ int ffmp_rollout(ffmp_handle *h, const int64_t *actions_dev, int32_t T, void *st
  *   - Fast path: the five bound device outputs are adjacent in memory in the order reward | rel_goal | velocity | done |
  *     flags, the five host destinations are adjacent in the same order (one 22*N-byte block each, 16-byte aligned, N even)
  *     and the host block is pinned (cudaHostAlloc / cudaHostRegister).  Then a small kernel queued behind the step writes
- *     the host block directly and publishes a completion word in mapped memory which the call spins on: no copy engine,
- *     no stream synchronisation.  Pinned action buffers are read in place by the step kernel.
+ *     the host block directly and publishes a completion word in mapped memory which the call spins on: no device-to-host
+ *     copy engine, no stream synchronisation.  The actions (8 N bytes) go in with one cudaMemcpyAsync.
  *   - Otherwise: cudaMemcpyAsync in, step, cudaMemcpyAsync out (one copy when both blocks are packed), stream sync.
- * FFMP_HOST_IO in the environment at ffmp_create selects the path: 0 copy engines, 1 mapped results with copied
- * actions, 2 (default) mapped results and in-place actions.
+ * FFMP_HOST_IO in the environment at ffmp_create selects the path: 0 copy engines both ways, 1 (default) mapped results,
+ * 2 mapped results and actions read in place over PCIe by the step kernel (faster on some hosts, slower on others:
+ * profiles/r01g_e2e_paths.txt, r01h_e2e_paths.txt).
  * ffmp_step_host = ffmp_step_host_async + ffmp_step_host_wait (gym.vector's step_async / step_wait): the host may
  * work between the two; exactly one wait per async.                                                             */
 int ffmp_step_host(ffmp_handle *h, const int64_t *actions_host, float *reward_host, uint8_t *done_host,
