@@ -480,7 +480,7 @@ int ffmp_step_host_async(ffmp_handle *h, const int64_t *actions_host, float *rew
                              reinterpret_cast<char *>(flags_host) == h0 + 21 * N;
     const bool packed = dev_packed && host_packed;
 
-    // mapped path: the export kernel writes the caller's pinned block and the completion word; no copy engine, no sync
+    // mapped path: the export kernel writes the caller's pinned block and the completion word; no device-to-host copy, no sync
     void *out_alias = nullptr;
     if (h->host_io >= 1 && packed && (22 * N) % 4 == 0 && reinterpret_cast<uintptr_t>(d0) % 16 == 0 &&
         reinterpret_cast<uintptr_t>(h0) % 16 == 0)

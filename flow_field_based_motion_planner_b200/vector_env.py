@@ -248,7 +248,7 @@ class FFMPVectorEnv:
     def step_host(self, actions_host):
         """Host-buffer step: actions int64[N] in (pinned) host memory -> (obs, reward, done, info) with reward,
         done, flags, relative_goal and velocity returned as host tensors; local_map stays on the device.
-        With pinned buffers nothing goes through a copy engine or a stream synchronisation (include/ffmp_b200.h)."""
+        With pinned buffers the results arrive without a device-to-host copy or a stream synchronisation (include/ffmp_b200.h)."""
         self.step_async(actions_host)
         return self.step_wait()
 
