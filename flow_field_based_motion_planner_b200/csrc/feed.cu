@@ -10,6 +10,8 @@
 // Flow control is credit based and collective-free: two buffers alternate by sequence parity, a consumer releases a buffer
 // by writing the sequence number it has finished reading into every producer's ack word, and a producer waits (a one-warp
 // spin kernel on its stream, bounded by a timeout) until the buffer it is about to overwrite has been released.
+#include <cstdlib>
+
 #include "ffmp_kernels.cuh"
 
 namespace ffmp {
@@ -121,7 +123,12 @@ cudaError_t launch_feed_signal(const FeedTargets &t, uint32_t mask, uint32_t val
 
 cudaError_t launch_feed_push(const FeedPushArgs &a, cudaStream_t st) {
     if (a.N <= 0 || a.ndst <= 0) return cudaSuccess;
-    const int grid = a.N < 148 * 4 ? a.N : 148 * 4;
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        const char *e = std::getenv("FFMP_FEED_CTAS_PER_SM");      // tuning knob (tools/feed_bench.py)
+        per_sm = e && std::atoi(e) > 0 ? std::atoi(e) : 4;
+    }
+    const int grid = a.N < 148 * per_sm ? a.N : 148 * per_sm;
     feed_push_kernel<<<grid, 256, 0, st>>>(a);
     return cudaGetLastError();
 }
