@@ -4,6 +4,7 @@ from .gym_compat import FFMP, make, register  # noqa: F401
 from .robot import NUM_ACTIONS, RobotAction, RobotPose, RobotState, RobotVelocity  # noqa: F401
 from .vector_env import FFMPConfig, FFMPVectorEnv, make_spaces, p_threshold  # noqa: F401
 from . import native, ops, spaces  # noqa: F401
+from .replay import ReplayRing  # noqa: F401
 
 __all__ = ["FFMP", "FFMPConfig", "FFMPVectorEnv", "RobotAction", "RobotPose", "RobotState", "RobotVelocity",
-           "NUM_ACTIONS", "make", "register", "make_spaces", "ops", "spaces", "native"]
+           "NUM_ACTIONS", "make", "register", "make_spaces", "ops", "spaces", "native", "ReplayRing"]

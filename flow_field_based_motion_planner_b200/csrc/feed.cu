@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(256) feed_push_kernel(FeedPushArgs a) {
             }
         }
     }
+    if (!a.ticket) return;            // local packing only (ffmp_pack_transitions): nothing to publish
     // ---- publish: the last CTA to finish writes the sequence number into every destination's flag word ----
     __threadfence_system();
     __syncthreads();

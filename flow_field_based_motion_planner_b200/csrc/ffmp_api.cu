@@ -792,6 +792,21 @@ int ffmp_feed_push(ffmp_handle *h, ffmp_feed *f, uint32_t dest_mask, double time
     return FFMP_OK;
 }
 
+int ffmp_pack_transitions(ffmp_handle *h, void *dst_dev, void *stream) {
+    if (!h || !dst_dev) return fail(FFMP_ERR_ARG, "null argument");
+    if (!h->ready) return fail(FFMP_ERR_STATE, "ffmp_reset must be called before ffmp_pack_transitions");
+    const ffmp_cfg &c = h->cfg;
+    if ((2 * c.window * c.window) % 16 || reinterpret_cast<uintptr_t>(dst_dev) % 16) return fail(FFMP_ERR_ARG, "dst must be 16-byte aligned and 2 W^2 a multiple of 16");
+    DeviceGuard guard(c.device);
+    ffmp::FeedPushArgs a{};
+    a.N = c.num_envs; a.K = c.ring; a.W = c.window; a.slot_new = h->p;
+    a.frames = h->b.frames; a.rel_goal = h->b.rel_goal; a.velocity = h->b.velocity; a.reward = h->b.reward; a.done = h->b.done;
+    a.ndst = 1; a.dst[0] = static_cast<uint8_t *>(dst_dev);
+    CK(ffmp::launch_feed_push(a, static_cast<cudaStream_t>(stream)));
+    h->launches += 1;
+    return FFMP_OK;
+}
+
 int ffmp_feed_wait(ffmp_feed *f, uint32_t src_mask, double timeout_s, void **buffer_dev, void *stream) {
     if (!f) return fail(FFMP_ERR_ARG, "feed is null");
     if (f->seq == 0) return fail(FFMP_ERR_STATE, "ffmp_feed_push must be called before ffmp_feed_wait (SPMD: every rank pushes every step)");

@@ -199,6 +199,11 @@ int ffmp_feed_release(ffmp_feed *f, uint32_t src_mask, void *stream);
 int ffmp_feed_error(ffmp_feed *f, uint32_t *out, void *stream);
 int ffmp_feed_destroy(ffmp_feed *f);
 
+/* The current transition block of the env, packed [maps u8 N*2*W*W | rel_goal f32 N*2 | velocity f32 N*2 | reward f32 N |
+ * done u8 N] (N * (2 W^2 + 21) bytes) into caller memory on this device: the storage step of a device replay ring
+ * (ReplayMemory.push, src/train.py:212-228) and the single-GPU form of ffmp_feed_push.  dst_dev: 16-byte aligned.  */
+int ffmp_pack_transitions(ffmp_handle *h, void *dst_dev, void *stream);
+
 /* ---- stateless operators (what the reference's external ROS nodes computed) ------------------- */
 
 /* Scenario generator (SPEC.md §3): for item n, env id env_gid_dev[n] (u32) and episode episode_dev[n]

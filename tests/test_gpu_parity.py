@@ -624,3 +624,34 @@ def test_env_checkpoint_resume_is_bit_identical(ffmp, cuda_device, planes):
         assert torch.equal(i1["flags"], i2["flags"]), t
     assert torch.equal(env.cost_field(), other.cost_field()) and torch.equal(env.flow_image(), other.flow_image())
     env.close(); other.close()
+
+
+def test_replay_ring_stores_and_samples_transitions(ffmp, cuda_device):
+    """Device replay ring (ReplayMemory / Transition, train.py:44,212-228): every stored field equals what the env returned
+    at that step, FIFO overwrite at capacity, samples only pair consecutive pushes that are both still resident."""
+    N, W, T = 16, 32, 6
+    env = ffmp.FFMPVectorEnv(N, seed=23, grid=64, window=W, ring=3, max_steps=9)
+    ring = ffmp.ReplayRing(env, T)
+    obs = env.reset()
+    ring.push()
+    log = [dict(m=obs["local_map"].clone(), g=obs["relative_goal"].clone(), v=obs["velocity"].clone(), a=None, r=None, d=None)]
+    rng = np.random.default_rng(6)
+    gen = torch.Generator(device=cuda_device); gen.manual_seed(1)
+    for t in range(1, 30):
+        a = torch.as_tensor(rng.integers(0, 28, N), device=cuda_device)
+        obs, reward, done, _ = env.step(a)
+        ring.push(a)
+        log.append(dict(m=obs["local_map"].clone(), g=obs["relative_goal"].clone(), v=obs["velocity"].clone(), a=a.clone(),
+                        r=reward.clone(), d=done.clone()))
+        assert len(ring) == (min(t + 1, T) - 1) * N
+        batch = ring.sample(64, generator=gen)
+        k, e = batch["index"][:, 0].tolist(), batch["index"][:, 1].tolist()
+        assert min(k) >= max(1, t - T + 2) and max(k) <= t
+        for b in range(64):
+            s0, s1 = log[k[b] - 1], log[k[b]]
+            assert torch.equal(batch["state_m"][b], s0["m"][e[b]]) and torch.equal(batch["observe_m"][b], s1["m"][e[b]])
+            assert torch.equal(batch["state_g"][b], s0["g"][e[b]]) and torch.equal(batch["observe_g"][b], s1["g"][e[b]])
+            assert torch.equal(batch["state_v"][b], s0["v"][e[b]]) and torch.equal(batch["observe_v"][b], s1["v"][e[b]])
+            assert batch["action"][b] == s1["a"][e[b]] and batch["reward"][b] == s1["r"][e[b]]
+            assert bool(batch["done"][b]) == bool(s1["d"][e[b]])
+    env.close()

@@ -85,6 +85,12 @@ def main():
     res["scan360_beams_per_s"] = N * 360 / (med * 1e-3)
     res["scan360_mean_range_m"] = float(sc[fin].mean().item())
     res["scan360_no_return_frac"] = float((~fin).float().mean().item())
+    # device replay ring: one push = the packed transition block of the whole batch
+    ring = ffmp.ReplayRing(env, 4)
+    med, _ = timed(lambda: ring.push())
+    res["replay_push_us"] = med * 1e3
+    res["replay_push_frac"] = 2 * ring.block / (med * 1e-3) / 6549.8e9
+    del ring
     acts = torch.randint(0, 28, (250, N), device=dev)
     for _ in range(2):
         env.rollout(acts)
