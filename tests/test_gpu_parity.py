@@ -655,3 +655,49 @@ def test_replay_ring_stores_and_samples_transitions(ffmp, cuda_device):
             assert batch["action"][b] == s1["a"][e[b]] and batch["reward"][b] == s1["r"][e[b]]
             assert bool(batch["done"][b]) == bool(s1["d"][e[b]])
     env.close()
+
+
+def test_rollout_full_size_properties(ffmp, cuda_device):
+    """BASELINE configs[2] at its full per-GPU size (4096 envs x 128 x 128, W = 100): size-independent properties instead of the
+    oracle — one batch of 4096 equals two shards of 2048 (global env ids), and every step's outputs are self-consistent."""
+    N, T = 4096, 120
+    kw = dict(grid=128, window=100, seed=77)
+    full = ffmp.FFMPVectorEnv(N, **kw)
+    lo = ffmp.FFMPVectorEnv(N // 2, env_id_base=0, **kw)
+    hi = ffmp.FFMPVectorEnv(N // 2, env_id_base=N // 2, **kw)
+    for env in (full, lo, hi):
+        env.reset()
+    gen = torch.Generator(device=cuda_device); gen.manual_seed(5)
+    ends = 0
+    for t in range(T):
+        a = torch.randint(0, 28, (N,), generator=gen, device=cuda_device)
+        obs, reward, done, info = full.step(a)
+        o1, r1, d1, i1 = lo.step(a[:N // 2].contiguous())
+        o2, r2, d2, i2 = hi.step(a[N // 2:].contiguous())
+        assert torch.equal(reward.view(torch.int32), torch.cat([r1, r2]).view(torch.int32)), t
+        assert torch.equal(done, torch.cat([d1, d2])), t
+        assert torch.equal(info["flags"], torch.cat([i1["flags"], i2["flags"]])), t
+        assert torch.equal(obs["relative_goal"].view(torch.int32), torch.cat([o1["relative_goal"], o2["relative_goal"]]).view(torch.int32)), t
+        flags = info["flags"]
+        assert torch.equal(done, flags != 0), t                                   # done = collision | goal | truncated
+        col, goal = (flags & 1) != 0, (flags & 2) != 0
+        # reward = (goal ? 1 : 0.05 (d_first - d)) + (col ? -1 : 0) - 0.05 (ffmp.py:130-157): bounded by the map diagonal
+        assert bool(((reward >= -1.05 - 0.05 * 10.0) & (reward <= 0.95 + 1e-6)).all()), t
+        assert bool((reward[goal & ~col] == 0.95).all()) and bool((reward[col & ~goal] <= -1.05 + 0.05 * 10.0).all()), t
+        assert bool((info["terminal_relative_goal"][:, 0][goal] < 0.5).all()), t   # is_goal: dist < 0.5 (ffmp.py:120-127)
+        assert bool((full.steps() <= 200).all()) and bool((full.steps()[done] == 0).all()), t
+        assert bool((obs["velocity"][done] == 0).all()), t                         # first tick of an episode (train.py:183-184)
+        lm = obs["local_map"]
+        assert bool((lm[:, 1, 50, 50] != 255).all()), t                            # the robot never stands on an occupied cell
+        assert bool((lm[done][:, 0] == lm[done][:, 1]).all()), t                   # both frames equal on the first tick (train.py:475-478)
+        ends += int(done.sum())
+        if t % 40 == 39:
+            assert torch.equal(obs["local_map"][:N // 2], o1["local_map"]) and torch.equal(obs["local_map"][N // 2:], o2["local_map"]), t
+    assert ends > 5000 and full.error_word() == 0
+    # the integration field of every current scenario: 0 at the goal cell, INF exactly on occupied cells of reached components
+    cost, occ = full.cost_field(), full.occupancy()
+    gc = full.scen.view(torch.int32)[full.episode().long() % full.config.slots, torch.arange(N, device=cuda_device)][:, 5:7].long()
+    assert bool((cost[torch.arange(N, device=cuda_device), gc[:, 0], gc[:, 1]] == 0).all())
+    assert bool((cost[occ != 0] == INF).all())
+    for env in (full, lo, hi):
+        env.close()
