@@ -269,8 +269,15 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
             uint32_t upF[WPR], dnF[WPR];
 #pragma unroll
             for (int w = 0; w < WPR; ++w) {
-                upF[w] = mask_on_fma(__shfl_up_sync(FULL, F[RPL - 1][w], 1), upm);
-                dnF[w] = mask_on_fma(__shfl_down_sync(FULL, F[0][w], 1), dnm);
+                if constexpr (GEN) {
+                    // generated scenarios have occupied border rows (SPEC.md §3) and empty padding rows: what lane 0 / lane 31
+                    // receive from themselves can only reach rows whose avail words are zero, so no boundary mask is needed
+                    upF[w] = __shfl_up_sync(FULL, F[RPL - 1][w], 1);
+                    dnF[w] = __shfl_down_sync(FULL, F[0][w], 1);
+                } else {
+                    upF[w] = mask_on_fma(__shfl_up_sync(FULL, F[RPL - 1][w], 1), upm);
+                    dnF[w] = mask_on_fma(__shfl_down_sync(FULL, F[0][w], 1), dnm);
+                }
             }
             uint32_t Nw[RPL][WPR];
 #pragma unroll
