@@ -327,6 +327,16 @@ def run_ours(a):
         v, dt = cpu_port_throughput(a, 256, 2400, 20, 1)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"256 envs x 2400 steps of the same workload, single thread, {dt:.1f} s (C oracle port, gcc -O2)"}
+        # the same port's flow field alone: queue BFS + 8-neighbour argmin on generated 128 x 128 maps
+        import oracle
+        maps = [oracle.scenario(a.seed, k, 0, a.grid, p_occ=a.p_occ) for k in range(64)]
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 2.0:
+            for occ_k, _, _, cells_k in maps:
+                oracle.flow_field(occ_k, cells_k[2], cells_k[3])
+            reps += 1
+        cpu["flow_field_cells_per_s"] = reps * len(maps) * a.grid * a.grid / (time.perf_counter() - t0)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
