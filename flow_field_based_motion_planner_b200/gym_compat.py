@@ -15,8 +15,10 @@ from .vector_env import (GOAL_THRESHOLD, MAP_GRID_NUM, MAP_RANGE, MAP_RESOLUTION
 
 
 class FFMP:
-    def __init__(self, device="cuda:0"):
+    def __init__(self, device="cuda:0", grid=MAP_GRID_NUM, seed=0, **env_kwargs):
         self.device = torch.device(device)
+        self._env_kwargs = dict(grid=grid, window=MAP_GRID_NUM, seed=seed, **env_kwargs)
+        self._env = None                                                          # 1-env FFMPVectorEnv behind reset() / step()
         self.action = RobotAction()
         self.action_space, self.observation_space, self.state_space = make_spaces(MAP_GRID_NUM)
         self.map_range, self.map_grid_num, self.map_grid_size = MAP_RANGE, MAP_GRID_NUM, MAP_RESOLUTION
@@ -74,6 +76,46 @@ class FFMP:
         r, d, f = ops.rewarder2(self._scan(scan_data).to(self.device), self._goal(relative_goal_info),
                                 self._first(is_first), self._d_first)
         return float(r.item()), bool(d.item()), bool(int(f.item()) & 2)
+
+
+    # ---- gym (Dec 2020, docker/Dockerfile:55) episode API: reset() -> obs, step(a) -> (obs, reward, done, info) ----------
+    # The reference never defined these (ffmp.py:77-83 is commented out; the episode lived in ROS nodes); here
+    # they drive one environment of the batched CUDA env (BASELINE config 1: one env on the reference's 100 x 100 map).
+    def _single(self):
+        if self._env is None:
+            self._env = FFMPVectorEnv(1, device=str(self.device), **self._env_kwargs)
+            self._act = torch.zeros(1, dtype=torch.int64).pin_memory()
+        return self._env
+
+    def _np_obs(self, obs):
+        lm = obs["local_map"][0].cpu().numpy()                                    # u8 [2, W, W]: older, newest
+        return {"local_map": lm[1].astype(np.int32)[:, :, None],                  # Box(0, 255, (100, 100, 1), int32), ffmp.py:40-58
+                "relative_goal": np.array(obs["relative_goal"][0].cpu().numpy(), dtype=np.float32),
+                "velocity": np.array(obs["velocity"][0].cpu().numpy(), dtype=np.float32)}, lm
+
+    def seed(self, seed=None):
+        if seed is not None:
+            self._env_kwargs["seed"] = int(seed)
+            self.close()
+        return [self._env_kwargs["seed"]]
+
+    def reset(self):
+        return self._np_obs(self._single().reset())[0]
+
+    def step(self, action):
+        """action: one of the 28 discrete ids the reference's agent emits (train.py:70,345,438)."""
+        env = self._single()
+        self._act[0] = int(action)
+        obs, reward, done, info = env.step_host(self._act)
+        o, stack = self._np_obs(obs)
+        flags = int(info["flags"][0])
+        return o, float(reward[0]), bool(done[0]), {"is_collision": bool(flags & 1), "is_goal": bool(flags & 2),
+                                                    "truncated": bool(flags & 4), "local_map_stack": stack}
+
+    def close(self):
+        if self._env is not None:
+            self._env.close()
+            self._env = None
 
 
 _REGISTRY = {}

@@ -701,3 +701,28 @@ def test_rollout_full_size_properties(ffmp, cuda_device):
     assert bool((cost[occ != 0] == INF).all())
     for env in (full, lo, hi):
         env.close()
+
+
+def test_single_env_gym_api_matches_oracle(ffmp):
+    """gym.make('FFMP-v0')-style object: reset() / step(action id) in the old 4-tuple API on the reference's 100 x 100 map
+    (BASELINE config 1), numpy observations with the declared shapes / dtypes, equal to the oracle step by step."""
+    env = ffmp.make("FFMP-v0", seed=7)
+    orc = oracle.OracleVectorEnv(1, grid=100, window=100, seed=7)
+    obs = env.reset(); orc.reset()
+    assert obs["local_map"].shape == (100, 100, 1) and obs["local_map"].dtype == np.int32
+    assert env.observation_space.spaces["local_map"].shape == (100, 100, 1)
+    assert np.array_equal(obs["local_map"][:, :, 0], orc.local_map[0, 1])
+    rng = np.random.default_rng(3)
+    ends = 0
+    for t in range(300):
+        a = int(rng.integers(0, 28))
+        obs, reward, done, info = env.step(a)
+        orc.step(np.array([a]))
+        assert np.float32(reward).view(np.uint32) == orc.reward.view(np.uint32)[0], t
+        assert done == bool(orc.done[0]) and info["is_collision"] == bool(orc.flags[0] & 1) and info["is_goal"] == bool(orc.flags[0] & 2), t
+        assert np.array_equal(obs["local_map"][:, :, 0], orc.local_map[0, 1]) and np.array_equal(info["local_map_stack"], orc.local_map[0]), t
+        assert np.array_equal(obs["relative_goal"].view(np.uint32), orc.rel_goal[0].view(np.uint32)), t
+        assert np.array_equal(obs["velocity"].view(np.uint32), orc.velocity[0].view(np.uint32)), t
+        ends += int(done)
+    assert ends >= 3
+    env.close()
