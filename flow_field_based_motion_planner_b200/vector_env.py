@@ -131,6 +131,7 @@ class FFMPVectorEnv:
         native.check(self._L.ffmp_bind(self._h, C.byref(b)), "ffmp_bind")
         self._done_bool = self.done.view(torch.bool)
         self._views = {}
+        self._host_out = {}
         self._host = None
         self._is_reset = False
 
@@ -225,25 +226,31 @@ class FFMPVectorEnv:
         if self._host is None:
             self._host_buffers()
         a = actions_host
-        if not (a.dtype == torch.int64 and a.device.type == "cpu" and a.numel() == self.num_envs and a.is_contiguous()):
+        if a.dtype is not torch.int64 or a.numel() != self.num_envs or a.device.type != "cpu" or not a.is_contiguous():
             raise ValueError("step_async expects a contiguous int64 CPU tensor with one action id per env")
         # the library switches to its own device (DeviceGuard): no torch device context here
-        rc = self._L.ffmp_step_host_async(self._h, a.data_ptr(), *self._host_ptrs, self._stream())
+        rc = self._L.ffmp_step_host_async(self._h, a.data_ptr(), *self._host_ptrs,
+                                          torch._C._cuda_getCurrentRawStream(self.device.index))
         if rc:
             native.check(rc, "ffmp_step_host_async")
-        self._pending_actions = a        # keeps the buffer alive while the kernel reads it in place
+        self._pending_actions = a        # keeps the buffer alive while the kernel reads it
 
     def step_wait(self):
         """gym.vector's step_wait: block until the step queued by step_async has delivered -> (obs, reward, done, info)
-        with reward, done, flags, relative_goal and velocity as pinned host tensors; local_map stays on the device."""
-        local_map = self._obs()["local_map"]           # host bookkeeping done while the GPU works
+        with reward, done, flags, relative_goal and velocity as pinned host tensors; local_map stays on the device.
+        The returned containers are cached per frame slot (do not mutate them)."""
+        p = C.c_int32()
+        self._L.ffmp_obs_slot(self._h, C.byref(p))                  # host bookkeeping done while the GPU works
+        out = self._host_out.get(p.value)
+        if out is None:
+            hst = self._host
+            obs = {"local_map": self._obs()["local_map"], "relative_goal": hst["rel_goal"], "velocity": hst["velocity"]}
+            out = self._host_out[p.value] = (obs, hst["reward"], hst["done_bool"], hst["info"])
         rc = self._L.ffmp_step_host_wait(self._h)
         if rc:
             native.check(rc, "ffmp_step_host_wait")
         self._pending_actions = None
-        hst = self._host
-        obs = {"local_map": local_map, "relative_goal": hst["rel_goal"], "velocity": hst["velocity"]}
-        return obs, hst["reward"], hst["done_bool"], hst["info"]
+        return out
 
     def step_host(self, actions_host):
         """Host-buffer step: actions int64[N] in (pinned) host memory -> (obs, reward, done, info) with reward,
