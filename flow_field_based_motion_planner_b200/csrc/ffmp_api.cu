@@ -120,6 +120,7 @@ struct ffmp_handle {
     int nlist = 1;
     cudaEvent_t ev_step[MAX_LISTS], ev_regen[MAX_LISTS];
     bool regen_pending[MAX_LISTS];
+    uint32_t regen_seq[MAX_LISTS];  // launches of list l so far; the kernel publishes it in mapped memory (flag_host[16 + l]) when done
     uint64_t step_index = 0;
     int p = 1;  // newest ring slot
     int ff_grid = 0;                // full-batch grid (reset)
@@ -145,8 +146,9 @@ struct ffmp_handle {
     cudaStream_t wait_stream = nullptr;
     // FFMP_HOST_IO_STATS=1: host / device timeline of the host-buffer steps, printed to stderr by ffmp_destroy
     bool io_stats = false;
-    double t_entry = 0, t_launched = 0, t_queued = 0;
+    double t_entry = 0, t_launched = 0, t_queued = 0, t_alias = 0, t_copyin = 0, t_tick = 0, t_evq = 0, acc9 = 0;
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double acc8 = 0;
     uint64_t acc_n = 0;
     unsigned long long *trace = nullptr;   // FFMP_TRACE=1: [N][8] tick-kernel timestamps (library-owned, diagnostics only)
 
@@ -201,15 +203,12 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
         // the regeneration that last used list `l` (S-1 ticks ago) must be complete: it re-armed the
         // list and filled the scenario slot an env may switch to in this tick.  If the host already sees it complete
         // (the usual case when the caller synchronises every step) no device-side wait is queued in front of the tick.
-        const cudaError_t q = cudaEventQuery(h->ev_regen[l]);
-        if (q == cudaErrorNotReady) {
-            cudaGetLastError();   // "not ready" is a status, not a failure: keep it out of the launchers' error checks
-            CK(cudaStreamWaitEvent(st, h->ev_regen[l], 0));
-        } else if (q != cudaSuccess) {
-            return fail(FFMP_ERR_CUDA, "cudaEventQuery(regeneration)", q);
-        }
+        // The regeneration kernel's last CTA publishes its launch number in mapped host memory: one plain load tells whether
+        // the launch has completed (a cudaEventQuery costs 1.7 us of host time in front of the step kernel's launch).
+        if (h->flag_host[16 + l] != h->regen_seq[l]) CK(cudaStreamWaitEvent(st, h->ev_regen[l], 0));
         h->regen_pending[l] = false;
     }
+    if (h->io_stats) h->t_evq = now_us();
     ffmp::StepArgs a = step_args(h);
     a.mode = mode; a.actions = actions; a.mask = mask;
     if (mode == 0) {
@@ -224,6 +223,7 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
     cudaEvent_t *tev = (h->timing && h->timing_n < ffmp_handle::TIMING_RING) ? h->tev[h->timing_n++] : nullptr;
     if (tev) CK(cudaEventRecord(tev[0], st));
     CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st, nullptr, h->fused, h->pipe, h->spec));
+    if (h->io_stats) h->t_tick = now_us();
     if (host_export) {
         // directly behind the step kernel (nothing in between), so that the programmatic dependency pairs the two
         CK(ffmp::launch_host_export(*host_export, st));
@@ -239,6 +239,8 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
     fa.env_idx = h->list_env(l); fa.episode = h->list_episode(l); fa.count_ptr = h->list_count(l);
     fa.ticket = h->list_ticket(l); fa.work = h->list_work(l); fa.count_reset = h->list_count(l);
     fa.hi_scratch = h->hi_scratch() + (static_cast<size_t>(h->ff_grid) + static_cast<size_t>(l) * h->rg_grid) * ffmp::flow_field_scratch_words(h->cfg.grid);
+    fa.host_done = h->flag_dev + 16 + l;
+    fa.host_done_value = ++h->regen_seq[l];
     CK(ffmp::launch_flow_field(fa, h->rg_grid, h->side[l]));
     if (tev) CK(cudaEventRecord(tev[3], h->side[l]));
     h->launches += 1;
@@ -288,7 +290,7 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
     h->ws = workspace_layout(cfg);
     h->nlist = cfg->slots - 1;
     std::memset(&h->b, 0, sizeof(h->b));
-    for (int i = 0; i < MAX_LISTS; ++i) { h->side[i] = nullptr; h->ev_step[i] = nullptr; h->ev_regen[i] = nullptr; h->regen_pending[i] = false; }
+    for (int i = 0; i < MAX_LISTS; ++i) { h->side[i] = nullptr; h->ev_step[i] = nullptr; h->ev_regen[i] = nullptr; h->regen_pending[i] = false; h->regen_seq[i] = 0; }
     std::memset(h->tev, 0, sizeof(h->tev));
     cudaError_t ce = cudaSuccess;
     for (int i = 0; i < h->nlist && ce == cudaSuccess; ++i) {
@@ -298,9 +300,9 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
     }
     if (ce == cudaSuccess) {
         void *fh = nullptr, *fd = nullptr;
-        ce = cudaHostAlloc(&fh, 64, cudaHostAllocMapped);
+        ce = cudaHostAlloc(&fh, 256, cudaHostAllocMapped);   // word 0 completion, words 2..7 stamps, words 16..31 regeneration lists
         if (ce == cudaSuccess) {
-            std::memset(fh, 0, 64);
+            std::memset(fh, 0, 256);
             h->flag_host = static_cast<volatile uint32_t *>(fh);
             ce = cudaHostGetDevicePointer(&fd, fh, 0);
             h->flag_dev = static_cast<uint32_t *>(fd);
@@ -380,6 +382,8 @@ int ffmp_destroy(ffmp_handle *h) {
     }
     if (h->io_stats && h->acc_n) {
         const double n = static_cast<double>(h->acc_n);
+        std::fprintf(stderr, "[ffmp host io] host us from entry: pointers classified %.2f | actions copy queued %.2f | regeneration event checked %.2f | step kernel submitted %.2f\n",
+                     h->acc[6] / n, h->acc[7] / n, h->acc9 / n, h->acc8 / n);
         std::fprintf(stderr, "[ffmp host io] steps %llu  us/step: submit step+export %.2f | all queued %.2f | results seen %.2f || "
                              "export resident->written %.2f (waiting for the step grid %.2f, copy+fence %.2f)\n",
                      static_cast<unsigned long long>(h->acc_n), h->acc[0] / n, h->acc[1] / n, h->acc[2] / n, h->acc[3] / n,
@@ -487,10 +491,12 @@ int ffmp_step_host_async(ffmp_handle *h, const int64_t *actions_host, float *rew
         out_alias = mapped_alias(h0);
     const int64_t *actions_dev = nullptr;
     if (out_alias && h->host_io >= 2) actions_dev = static_cast<const int64_t *>(mapped_alias(actions_host));
+    if (h->io_stats) h->t_alias = now_us();
     if (!actions_dev) {
         CK(cudaMemcpyAsync(h->actions(), actions_host, N * sizeof(int64_t), cudaMemcpyHostToDevice, st));
         actions_dev = h->actions();
     }
+    if (h->io_stats) h->t_copyin = now_us();
     if (out_alias) {
         ffmp::HostExportArgs ea{};
         ea.src = d0; ea.dst = out_alias;
@@ -560,6 +566,10 @@ int ffmp_step_host_wait(ffmp_handle *h) {
         h->acc[3] += g2 - g0;                      // export kernel resident -> block written
         h->acc[4] += g1 - g0;                      // export kernel resident -> step grid complete
         h->acc[5] += g2 - g1;                      // step grid complete -> block written
+        h->acc[6] += h->t_alias - h->t_entry;      // entry -> pointer classification done
+        h->acc[7] += h->t_copyin - h->t_entry;     // entry -> actions copy queued
+        h->acc8 += h->t_tick - h->t_entry;         // entry -> step kernel submitted
+        h->acc9 += h->t_evq - h->t_entry;          // entry -> regeneration event checked
         h->acc_n += 1;
     }
     return FFMP_OK;

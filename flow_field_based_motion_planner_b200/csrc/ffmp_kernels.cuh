@@ -44,6 +44,8 @@ struct FlowArgs {
     uint64_t seed;
     uint32_t *scen_out;
     uint32_t neg1, one;         // 0xFFFFFFFF and 1 (set by the launcher): opaque IMAD multipliers, see flow_field.cu
+    uint32_t *host_done;        // optional word in mapped host memory: the last CTA publishes host_done_value there, so the host
+    uint32_t host_done_value;   //   can tell without a CUDA call that this (background regeneration) launch has completed
 };
 
 struct StepArgs {

@@ -667,6 +667,10 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
             if (a.work) *a.work = 0;
             if (a.count_reset) *a.count_reset = 0;
             __threadfence();
+            if (a.host_done) {       // every CTA fenced its writes before it took its ticket: the launch's results are visible
+                __threadfence_system();
+                *reinterpret_cast<volatile uint32_t *>(a.host_done) = a.host_done_value;
+            }
         }
     }
 }
