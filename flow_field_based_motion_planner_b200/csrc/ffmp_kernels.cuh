@@ -26,6 +26,7 @@ struct FlowArgs {
     const uint32_t *env_idx;    // dev u32[count] or null
     const uint32_t *episode;    // dev u32[count] or null (use episode_const; slot_mode only)
     const uint32_t *count_ptr;  // dev count or null
+    const uint32_t *order;      // dev u32[count] or null: hand-out position -> item (deepest grids first, see flow_order.cu)
     int count;
     uint32_t episode_const;
     int G, slot_mode, S, N;

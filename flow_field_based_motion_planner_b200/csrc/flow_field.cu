@@ -690,6 +690,11 @@ static bool rows_for_small() {
     return e && std::atoi(e) != 0;
 }
 cudaError_t launch_flow_field_large(const FlowArgs &a, int grid, cudaStream_t st);
+cudaError_t launch_flow_field_il(const FlowArgs &a, int grid, cudaStream_t st);      // flow_field_il.cu: 96 < G <= 128
+static bool il_v2() {        // development switch: FFMP_FLOW_V2=1 keeps the round-1 kernel for 96 < G <= 128 (A/B measurements)
+    const char *e = std::getenv("FFMP_FLOW_V2");
+    return e && std::atoi(e) != 0;
+}
 
 bool flow_field_supported(int G) { return (G >= 16 && G <= 128 && (G % 4) == 0) || flow_field_large_supported(G); }
 
@@ -707,6 +712,10 @@ int flow_field_max_grid(int G) {
     const int smem = (nps_of(false) + 2) * 32 * wpr * wpr * 4 + (wpr == 4 ? 16 : 32 * 32 * wpr) + 1024 + 16;
     int per_sm = (227 * 1024) / smem;
     if (per_sm > 16) per_sm = 16;            // __launch_bounds__(32, 16): 128 registers per thread
+    if (const char *e = std::getenv("FFMP_FLOW_CTAS")) {      // development switch: fewer resident warps per SM
+        const int c = std::atoi(e);
+        if (c >= 1 && c < per_sm) per_sm = c;
+    }
     return 148 * per_sm;
 }
 
@@ -718,6 +727,7 @@ cudaError_t launch_flow_field(const FlowArgs &a_in, int grid, cudaStream_t st) {
     a.one = 1u;
     const int wpr = (a.G + 31) / 32;
     if (a.work && !a.ticket) return cudaErrorInvalidValue;   // the work counter is re-armed by the ticket holder
+    if (wpr == 4 && !il_v2()) return launch_flow_field_il(a, grid, st);
     if (a.generate) {
         switch (wpr) {
         case 1: flow_field_warp_kernel<1, true><<<grid, 32, 0, st>>>(a); break;
