@@ -128,8 +128,6 @@ struct ffmp_handle {
     CUtensorMap tmap;               // flow planes as a 3-D u8 tensor for the TMA observe kernel
     bool use_tma = false;
     bool fused = true;              // one kernel per tick (env FFMP_STEP_FUSED=0 selects dynamics + observe kernels)
-    bool pipe = false;              // FFMP_TICK_PIPE=1: steps use the experimental tick_pipe_kernel instead of tick_tma_kernel
-    bool spec = false;              // FFMP_TICK_SPEC=1: steps use the experimental tick_spec_kernel (speculative drain)
     // optional per-kernel timing (ffmp_timing): events [before tick, after tick] on the caller's stream and
     // [before regeneration, after regeneration] on the side stream of the tick
     static constexpr int TIMING_RING = 256;
@@ -222,7 +220,7 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
     const bool one_kernel = h->use_tma && h->fused;
     cudaEvent_t *tev = (h->timing && h->timing_n < ffmp_handle::TIMING_RING) ? h->tev[h->timing_n++] : nullptr;
     if (tev) CK(cudaEventRecord(tev[0], st));
-    CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st, nullptr, h->fused, h->pipe, h->spec));
+    CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st, nullptr, h->fused));
     if (h->io_stats) h->t_tick = now_us();
     if (host_export) {
         // directly behind the step kernel (nothing in between), so that the programmatic dependency pairs the two
@@ -283,8 +281,6 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
     if (!h) return fail(FFMP_ERR_ARG, "out of host memory");
     h->cfg = *cfg;
     if (const char *f = std::getenv("FFMP_STEP_FUSED")) h->fused = std::atoi(f) != 0;
-    if (const char *f = std::getenv("FFMP_TICK_PIPE")) h->pipe = std::atoi(f) != 0;
-    if (const char *f = std::getenv("FFMP_TICK_SPEC")) h->spec = std::atoi(f) != 0;
     if (const char *f = std::getenv("FFMP_HOST_IO")) h->host_io = std::atoi(f);
     if (const char *f = std::getenv("FFMP_HOST_IO_STATS")) h->io_stats = std::atoi(f) != 0;
     h->ws = workspace_layout(cfg);
@@ -906,8 +902,9 @@ int ffmp_op_scenarios(int32_t device, int32_t n, int32_t G, uint32_t p_thresh, i
 size_t ffmp_op_flow_field_workspace(int32_t n, int32_t G) {
     if (n <= 0 || !ffmp::flow_field_supported(G)) return 0;
     const int maxg = ffmp::flow_field_max_grid(G);
-    // 256-byte header (work counter, completion ticket) + the per-CTA plane scratch
-    return 256 + static_cast<size_t>(n < maxg ? n : maxg) * ffmp::flow_field_scratch_words(G) * 4;
+    // 256-byte header (work counter, completion ticket) + the per-CTA plane scratch + the hand-out order of the batch
+    return 256 + align_up(static_cast<size_t>(n < maxg ? n : maxg) * ffmp::flow_field_scratch_words(G) * 4, 256) +
+           static_cast<size_t>(n) * sizeof(uint32_t);
 }
 
 int ffmp_op_flow_field(int32_t device, int32_t n, int32_t G, const uint8_t *occ_dev, const int32_t *goal_cells_dev,
@@ -919,16 +916,25 @@ int ffmp_op_flow_field(int32_t device, int32_t n, int32_t G, const uint8_t *occ_
         return fail(FFMP_ERR_ARG, "occ / cost / flow must be 16-byte aligned");
     if (int rc = check_device(device)) return rc;
     DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     ffmp::FlowArgs a{};
     a.count = n; a.G = G; a.slot_mode = 0; a.S = 1; a.N = n;
     a.occ = occ_dev; a.goal_cells = goal_cells_dev; a.cost = cost_dev; a.flow = flow_dev;
     if (reinterpret_cast<uintptr_t>(workspace_dev) % 16) return fail(FFMP_ERR_ARG, "workspace must be 16-byte aligned");
-    CK(cudaMemsetAsync(workspace_dev, 0, 16, static_cast<cudaStream_t>(stream)));
+    CK(cudaMemsetAsync(workspace_dev, 0, 16, st));
     a.work = static_cast<uint32_t *>(workspace_dev);       // dynamic grid hand-out counter + completion ticket
     a.ticket = a.work + 1;
     a.hi_scratch = static_cast<uint32_t *>(workspace_dev) + 64;
     const int maxg = ffmp::flow_field_max_grid(G);
-    CK(ffmp::launch_flow_field(a, n < maxg ? n : maxg, static_cast<cudaStream_t>(stream)));
+    const int grid = n < maxg ? n : maxg;
+    if (n >= 2 * grid) {
+        // several grids per warp / CTA: deepest grids first (flow_order.cu)
+        uint32_t *order = reinterpret_cast<uint32_t *>(static_cast<char *>(workspace_dev) + 256 +
+                                                       align_up(static_cast<size_t>(grid) * ffmp::flow_field_scratch_words(G) * 4, 256));
+        CK(ffmp::launch_flow_order(goal_cells_dev, n, G, order, st));
+        a.order = order;
+    }
+    CK(ffmp::launch_flow_field(a, grid, st));
     return FFMP_OK;
 }
 

@@ -137,11 +137,11 @@ cudaError_t launch_scan(const ScanArgs &a, cudaStream_t st);                // s
 cudaError_t launch_learner_input(const FeedArgs &a, cudaStream_t st);
 cudaError_t launch_scenarios(const ScenarioArgs &a, int grid, cudaStream_t st);
 cudaError_t launch_flow_field(const FlowArgs &a, int grid, cudaStream_t st);
+cudaError_t launch_flow_order(const int32_t *goal_cells, int n, int G, uint32_t *order, cudaStream_t st);   // flow_order.cu
 // tmap: TMA descriptor of the flow planes [S*N][G][G] (box W x ceil16(W)) or null -> plain-load observe kernel
 // fused: run the scalar step inside the TMA observe kernel (one launch per tick); ignored without a tensor map
-// spec: mode-0 ticks run tick_spec_kernel (speculative drain); pipe: the persistent producer / consumer tick_pipe_kernel
 cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t st, cudaEvent_t between = nullptr,
-                        bool fused = true, bool pipe = false, bool spec = false);
+                        bool fused = true);
 cudaError_t launch_rewarder(const RewarderArgs &a, cudaStream_t st);
 int flow_field_max_grid(int G);            // resident CTAs for a full wave (multiple of the SM count)
 size_t flow_field_scratch_words(int G);    // hi_scratch words per CTA

@@ -1,4 +1,5 @@
-// flow_field.cu — SPEC.md §4/§5: integration field (F1), flow direction (F2) and flow image, G <= 128.
+// flow_field.cu — SPEC.md §4/§5: integration field (F1), flow direction (F2) and flow image, G <= 96 (linear bit layout;
+// 96 < G <= 128 is served by flow_field_il.cu, 128 < G <= 512 by flow_field_large.cu) and the launcher of all three.
 // Replaces the external /bev/* flow-image ROS node (/root/reference/src/train.py:84,116-121).
 //
 // Design (one WARP per grid, no block barrier anywhere):
@@ -51,17 +52,14 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
     constexpr int NPLX = NPS + 2;               // + visited / free planes for the post-BFS phases
     constexpr int PVIS = NPS, PFREE = NPS + 1;
     constexpr int RPL = WPR;                    // rows per lane
-    // G in (96, 128]: the four words of a row hold the columns c % 4 == w (bit b <-> column 4b + w), so the horizontal
-    // neighbours of the wavefront step are the neighbouring words themselves and only 2 of 8 per row need a shift
-    constexpr bool IL = WPR == 4;
+    static_assert(WPR <= 3, "96 < G <= 128 is served by flow_field_il.cu");
     constexpr int P = 32 * WPR;                 // padded grid side
     constexpr int PLANE_WORDS = 32 * RPL * WPR;  // one bit-plane of the padded grid
     constexpr int CH = 2 * WPR;                 // 16-byte chunks per staged byte row
     constexpr bool SWZ = (CH & (CH - 1)) == 0;
-    // cost-byte staging of one pass (32 rows x P bytes): WPR == 4 reuses dead plane storage (the free plane + the
-    // (k, r) slices of planes 0..3 just read), smaller grids have a dedicated buffer
-    constexpr bool INPLACE = WPR == 4;
-    constexpr int STAGE_WORDS = INPLACE ? 4 : 8 * P;
+    // cost-byte staging of one pass (32 rows x P bytes)
+    constexpr bool INPLACE = false;
+    constexpr int STAGE_WORDS = 8 * P;
     __shared__ __align__(128) uint32_t pl[NPLX * PLANE_WORDS];
     __shared__ __align__(16) uint32_t stage_buf[STAGE_WORDS];
     __shared__ __align__(8) uint64_t mbar;
@@ -96,6 +94,7 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
             item = __shfl_sync(FULL, item, 0);
         }
         if (item >= count) break;
+        if (a.order) item = static_cast<int>(a.order[item]);
         const uint32_t env = a.env_idx ? a.env_idx[item] : static_cast<uint32_t>(item);
         const size_t cells = static_cast<size_t>(G) * G;
         size_t plane;
@@ -117,19 +116,10 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
             sp.gi = __shfl_sync(FULL, sp.gi, 0); sp.gj = __shfl_sync(FULL, sp.gj, 0);
             gi = sp.gi; gj = sp.gj;
             // rolled loop (code size): the free words go to their plane and are read back as rows below
-            if constexpr (IL) {
 #pragma unroll 1
-                for (int r = 0; r < RPL; ++r) {
-                    uint32_t fr[4];
-                    scenario_free_row_il(key, lane * RPL + r, G, a.block_shift, a.p_thresh, sp, fr);
-                    *reinterpret_cast<uint4 *>(&pl[pidx(PFREE, r, lane)]) = make_uint4(fr[0], fr[1], fr[2], fr[3]);
-                }
-            } else {
-#pragma unroll 1
-                for (int rw = 0; rw < RPL * WPR; ++rw) {
-                    const int r = rw / WPR, w = rw - r * WPR;
-                    pl[pidx(PFREE, r, lane) + w] = scenario_free_word(key, lane * RPL + r, 32 * w, G, a.block_shift, a.p_thresh, sp);
-                }
+            for (int rw = 0; rw < RPL * WPR; ++rw) {
+                const int r = rw / WPR, w = rw - r * WPR;
+                pl[pidx(PFREE, r, lane) + w] = scenario_free_word(key, lane * RPL + r, 32 * w, G, a.block_shift, a.p_thresh, sp);
             }
 #pragma unroll
             for (int r = 0; r < RPL; ++r) Row<WPR>::ld(&pl[pidx(PFREE, r, lane)], A[r]);
@@ -156,8 +146,7 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
             // ---- 2. bytes -> free-cell bit mask: one byte per lane and one warp vote per 32 cells; the vote lands in
             //      the register of the lane that owns the row (static register indices, rolled over the owner lane) ----
             {
-                // interleaved layout: lane l votes for column 4l + w, so the vote IS the interleaved word w
-                const uint8_t *stage = reinterpret_cast<const uint8_t *>(pl) + (IL ? 4 * lane : lane);
+                const uint8_t *stage = reinterpret_cast<const uint8_t *>(pl) + lane;
                 if (G == 32 * WPR) {
                     // exact fit: word (R, w) is the 32 bytes at (R * WPR + w) * 32; per word LDS.U8, compare, vote, select
 #pragma unroll 1
@@ -168,7 +157,7 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
                         for (int r = 0; r < RPL; ++r)
 #pragma unroll
                             for (int w = 0; w < WPR; ++w) {
-                                const uint32_t bits = __ballot_sync(FULL, src[IL ? r * WPR * 32 + w : (r * WPR + w) * 32] == 0);
+                                const uint32_t bits = __ballot_sync(FULL, src[(r * WPR + w) * 32] == 0);
                                 if (mine) A[r][w] = bits;
                             }
                     }
@@ -181,8 +170,8 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
                             const int R = o * RPL + r;
 #pragma unroll
                             for (int w = 0; w < WPR; ++w) {
-                                const int col = IL ? 4 * lane + w : 32 * w + lane;
-                                const bool fr = (R < G && col < G) ? stage[R * G + (IL ? w : 32 * w)] == 0 : false;
+                                const int col = 32 * w + lane;
+                                const bool fr = (R < G && col < G) ? stage[R * G + 32 * w] == 0 : false;
                                 const uint32_t bits = __ballot_sync(FULL, fr);
                                 if (mine) A[r][w] = bits;
                             }
@@ -214,8 +203,8 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
         {
             // goal seeding with static register indices only (a conditional on (r, w) would turn A / F into local arrays)
             const bool ok = gi >= 0 && gj >= 0 && gi < G && gj < G && lane == gi / RPL;
-            const int gr = gi % RPL, gw = IL ? (gj & 3) : (gj >> 5);
-            const uint32_t bit = ok ? (1u << (IL ? (gj >> 2) : (gj & 31))) : 0u;
+            const int gr = gi % RPL, gw = gj >> 5;
+            const uint32_t bit = ok ? (1u << (gj & 31)) : 0u;
 #pragma unroll
             for (int r = 0; r < RPL; ++r)
 #pragma unroll
@@ -286,7 +275,7 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
                 for (int w = 0; w < WPR; ++w) {
                     const uint32_t up = r == 0 ? upF[w] : F[r - 1][w];
                     const uint32_t dn = r == RPL - 1 ? dnF[w] : F[r + 1][w];
-                    Nw[r][w] = (from_lo<WPR, IL>(F[r], w) | from_hi<WPR, IL>(F[r], w) | up | dn) & A[r][w];
+                    Nw[r][w] = (from_lo<WPR>(F[r], w) | from_hi<WPR>(F[r], w) | up | dn) & A[r][w];
                 }
 #pragma unroll
             for (int r = 0; r < RPL; ++r)
@@ -413,7 +402,6 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
                 Row<WPR>::ld(&pl[pidx(PFREE, rd, ld)], Fd);
             }
             const int R = lane * RPL + r;
-            uint32_t D0[IL ? WPR : 1], D1[IL ? WPR : 1], D2[IL ? WPR : 1], D3[IL ? WPR : 1];   // interleaved: the row's planes
 #pragma unroll
             for (int w = 0; w < WPR; ++w) {
                 const uint32_t own = Vc[w];
@@ -422,14 +410,14 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
                 // orthogonal neighbours one level lower (codes 0 E, 2 N, 4 W, 6 S)
                 const uint32_t lE = own & Vd[w] & ~(b1d[w] ^ t);
                 const uint32_t lW = own & Vu[w] & ~(b1u[w] ^ t);
-                const uint32_t lN = own & from_hi<WPR, IL>(Vc, w) & ~(from_hi<WPR, IL>(b1c, w) ^ t);
-                const uint32_t lS = own & from_lo<WPR, IL>(Vc, w) & ~(from_lo<WPR, IL>(b1c, w) ^ t);
+                const uint32_t lN = own & from_hi<WPR>(Vc, w) & ~(from_hi<WPR>(b1c, w) ^ t);
+                const uint32_t lS = own & from_lo<WPR>(Vc, w) & ~(from_lo<WPR>(b1c, w) ^ t);
                 // admissible diagonals two levels lower (codes 1 NE, 3 NW, 5 SW, 7 SE)
-                const uint32_t fE = Fd[w], fW = Fu[w], fN = from_hi<WPR, IL>(Fc, w), fS = from_lo<WPR, IL>(Fc, w);
-                const uint32_t lNE = own & from_hi<WPR, IL>(Fd, w) & fE & fN & (from_hi<WPR, IL>(b1d, w) ^ b1c[w]) & ~(from_hi<WPR, IL>(b2d, w) ^ u);
-                const uint32_t lNW = own & from_hi<WPR, IL>(Fu, w) & fW & fN & (from_hi<WPR, IL>(b1u, w) ^ b1c[w]) & ~(from_hi<WPR, IL>(b2u, w) ^ u);
-                const uint32_t lSW = own & from_lo<WPR, IL>(Fu, w) & fW & fS & (from_lo<WPR, IL>(b1u, w) ^ b1c[w]) & ~(from_lo<WPR, IL>(b2u, w) ^ u);
-                const uint32_t lSE = own & from_lo<WPR, IL>(Fd, w) & fE & fS & (from_lo<WPR, IL>(b1d, w) ^ b1c[w]) & ~(from_lo<WPR, IL>(b2d, w) ^ u);
+                const uint32_t fE = Fd[w], fW = Fu[w], fN = from_hi<WPR>(Fc, w), fS = from_lo<WPR>(Fc, w);
+                const uint32_t lNE = own & from_hi<WPR>(Fd, w) & fE & fN & (from_hi<WPR>(b1d, w) ^ b1c[w]) & ~(from_hi<WPR>(b2d, w) ^ u);
+                const uint32_t lNW = own & from_hi<WPR>(Fu, w) & fW & fN & (from_hi<WPR>(b1u, w) ^ b1c[w]) & ~(from_hi<WPR>(b2u, w) ^ u);
+                const uint32_t lSW = own & from_lo<WPR>(Fu, w) & fW & fS & (from_lo<WPR>(b1u, w) ^ b1c[w]) & ~(from_lo<WPR>(b2u, w) ^ u);
+                const uint32_t lSE = own & from_lo<WPR>(Fd, w) & fE & fS & (from_lo<WPR>(b1d, w) ^ b1c[w]) & ~(from_lo<WPR>(b2d, w) ^ u);
                 const uint32_t anyD = lNE | lNW | lSW | lSE;
                 const uint32_t m0 = (anyD & lNE) | (~anyD & lE);
                 const uint32_t m1 = (anyD & lNW) | (~anyD & lN);
@@ -439,9 +427,7 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
                 const uint32_t d1 = ~m0 & (m1 | (~m2 & m3));
                 const uint32_t d2 = ~m0 & ~m1 & (m2 | m3);
                 const uint32_t d3 = ~(m0 | m1 | m2 | m3);
-                if constexpr (IL) {
-                    D0[w] = anyD; D1[w] = d1; D2[w] = d2; D3[w] = d3;
-                } else if (R < G && 32 * w < G) {
+                if (R < G && 32 * w < G) {
                     uint32_t out[8];
                     flow_bytes32(anyD, d1, d2, d3, ~Fc[w], out);
                     uint8_t *dst = flow + static_cast<size_t>(R) * G + 32 * w;
@@ -455,25 +441,6 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
                             for (int n = 0; n < 4; ++n)
                                 if (col0 + 4 * n < G) *reinterpret_cast<uint32_t *>(dst + 16 * c + 4 * n) = out[4 * c + n];
                         }
-                    }
-                }
-            }
-            if constexpr (IL) {
-                if (R < G) {
-                    uint32_t occ[4], out[32];
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) occ[w] = ~Fc[w];
-                    flow_bytes128_il(D0, D1, D2, D3, occ, out);        // out[n] = columns 4n .. 4n+3 of the row
-                    uint8_t *dst = flow + static_cast<size_t>(R) * G;
-                    if ((G & 15) == 0) {                               // rows are 16-byte aligned only if G % 16 == 0
-#pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            if (16 * c < G)
-                                *reinterpret_cast<uint4 *>(dst + 16 * c) = make_uint4(out[4 * c], out[4 * c + 1], out[4 * c + 2], out[4 * c + 3]);
-                    } else {
-#pragma unroll
-                        for (int n = 0; n < 32; ++n)
-                            if (4 * n < G) *reinterpret_cast<uint32_t *>(dst + 4 * n) = out[n];
                     }
                 }
             }
@@ -513,48 +480,6 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
                             return reinterpret_cast<uint8_t *>(stage_buf) + o;
                         }
                     };
-                    if constexpr (IL) {
-                        // interleaved: byte j of transpose8(word w, byte group b) is the cost of column 4(8b+j)+w, so a 4x4 byte
-                        // transpose across the four words yields the 32 consecutive columns 32b .. 32b+31 (chunks 2b, 2b+1)
-                        uint32_t tl[4][4], th[4][4], Vr[WPR];
-                        const int Rr = lane * RPL + r;
-                        Row<WPR>::ld(&pl[pidx(PVIS, r, lane)], Vr);
-#pragma unroll
-                        for (int w = 0; w < 4; ++w) {
-                            bytes4x4(Bk[0][w], Bk[1][w], Bk[2][w], Bk[3][w], tl[w]);
-                            bytes4x4(Bk[4][w], Bk[5][w], Bk[6][w], Bk[7][w], th[w]);
-                        }
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            uint32_t lo[4], hb[4], x[4], y[4];
-#pragma unroll
-                            for (int w = 0; w < 4; ++w) {
-                                lo[w] = tl[w][b]; hb[w] = th[w][b];
-                                transpose8(lo[w], hb[w]);
-                            }
-                            bytes4x4(lo[0], lo[1], lo[2], lo[3], x);
-                            bytes4x4(hb[0], hb[1], hb[2], hb[3], y);
-                            // x[j] / y[j] = the cost bytes of columns 4n .. 4n+3 with n = 8b + j / 8b + 4 + j; their visited bits are
-                            // bit n of the row's four interleaved words.  The lane widens and stores its own row: the 32 16-byte
-                            // stores of a row fill its four 128-byte lines (no staging, no second pass over shared memory).
-                            if (Rr < G) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const int n = 8 * b + j;
-                                    if (4 * n < G) {
-                                        const uint32_t b4 = j < 4 ? x[j & 3] : y[j & 3];
-                                        const uint32_t bit = 1u << n;
-                                        int4 c;
-                                        c.x = (Vr[0] & bit) ? static_cast<int>(__byte_perm(b4, 0u, 0x4440)) : COST_INF;
-                                        c.y = (Vr[1] & bit) ? static_cast<int>(__byte_perm(b4, 0u, 0x4441)) : COST_INF;
-                                        c.z = (Vr[2] & bit) ? static_cast<int>(__byte_perm(b4, 0u, 0x4442)) : COST_INF;
-                                        c.w = (Vr[3] & bit) ? static_cast<int>(__byte_perm(b4, 0u, 0x4443)) : COST_INF;
-                                        *reinterpret_cast<int4 *>(cost + static_cast<size_t>(Rr) * G + 4 * n) = c;
-                                    }
-                                }
-                            }
-                        }
-                    } else {
 #pragma unroll
                     for (int w = 0; w < WPR; ++w) {
                         uint32_t tl[4], th[4];
@@ -575,10 +500,9 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
                                 make_uint4(out[4 * c], out[4 * c + 1], out[4 * c + 2], out[4 * c + 3]);
                         }
                     }
-                    }
                     __syncwarp();
                     const int col = 4 * lane;
-                    if (!IL && col < G) {
+                    if (col < G) {
 #pragma unroll 4
                         for (int i = 0; i < 32; ++i) {
                             const int R = i * RPL + r;
@@ -587,13 +511,7 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
                             const int sw = SWZ ? (chunk ^ ((i / (8 / CH)) % CH)) : chunk;
                             const uint32_t b4 = *reinterpret_cast<const uint32_t *>(phys(i * P + 16 * sw + (col & 15)));
                             uint32_t vb;
-                            if constexpr (IL) {   // columns 4 lane .. 4 lane + 3 are bit `lane` of the row's four words
-                                const uint4 v4 = *reinterpret_cast<const uint4 *>(&pl[pidx(PVIS, r, i)]);
-                                vb = ((v4.x >> lane) & 1u) | (((v4.y >> lane) & 1u) << 1) | (((v4.z >> lane) & 1u) << 2) |
-                                     (((v4.w >> lane) & 1u) << 3);
-                            } else {
-                                vb = pl[pidx(PVIS, r, i) + (col >> 5)] >> (col & 31);
-                            }
+                            vb = pl[pidx(PVIS, r, i) + (col >> 5)] >> (col & 31);
                             int4 c;
                             c.x = (vb & 1u) ? static_cast<int>(b4 & 0xFFu) : COST_INF;
                             c.y = (vb & 2u) ? static_cast<int>((b4 >> 8) & 0xFFu) : COST_INF;
@@ -605,21 +523,6 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
                     __syncwarp();
                 }
             } else {
-                if constexpr (IL) {
-                    // deep maps (>= 256 levels, rare): put the cost planes and the visited plane back into the linear layout
-#pragma unroll 1
-                    for (int k = 0; k <= kmax; ++k) {
-#pragma unroll 1
-                        for (int r = 0; r < RPL; ++r) {
-                            uint32_t *p = k < kmax ? plane_ptr(k, r, lane) : &pl[pidx(PVIS, r, lane)];
-                            uint32_t v[4];
-                            v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[3] = p[3];
-                            row_to_linear(v);
-                            p[0] = v[0]; p[1] = v[1]; p[2] = v[2]; p[3] = v[3];
-                        }
-                    }
-                    __syncwarp();
-                }
 #pragma unroll 1
                 for (int rw = 0; rw < RPL * WPR; ++rw) {
                     const int r = rw / WPR, w = rw - r * WPR;
@@ -691,10 +594,6 @@ static bool rows_for_small() {
 }
 cudaError_t launch_flow_field_large(const FlowArgs &a, int grid, cudaStream_t st);
 cudaError_t launch_flow_field_il(const FlowArgs &a, int grid, cudaStream_t st);      // flow_field_il.cu: 96 < G <= 128
-static bool il_v2() {        // development switch: FFMP_FLOW_V2=1 keeps the round-1 kernel for 96 < G <= 128 (A/B measurements)
-    const char *e = std::getenv("FFMP_FLOW_V2");
-    return e && std::atoi(e) != 0;
-}
 
 bool flow_field_supported(int G) { return (G >= 16 && G <= 128 && (G % 4) == 0) || flow_field_large_supported(G); }
 
@@ -706,16 +605,14 @@ size_t flow_field_scratch_words(int G) {
     return static_cast<size_t>(NPG) * 32 * wpr * wpr;
 }
 
+int flow_field_il_ctas_per_sm();
 int flow_field_max_grid(int G) {
     if (G > 128) return flow_field_large_max_grid(G);
     const int wpr = (G + 31) / 32;
+    if (wpr == 4) return 148 * flow_field_il_ctas_per_sm();
     const int smem = (nps_of(false) + 2) * 32 * wpr * wpr * 4 + (wpr == 4 ? 16 : 32 * 32 * wpr) + 1024 + 16;
     int per_sm = (227 * 1024) / smem;
     if (per_sm > 16) per_sm = 16;            // __launch_bounds__(32, 16): 128 registers per thread
-    if (const char *e = std::getenv("FFMP_FLOW_CTAS")) {      // development switch: fewer resident warps per SM
-        const int c = std::atoi(e);
-        if (c >= 1 && c < per_sm) per_sm = c;
-    }
     return 148 * per_sm;
 }
 
@@ -727,13 +624,12 @@ cudaError_t launch_flow_field(const FlowArgs &a_in, int grid, cudaStream_t st) {
     a.one = 1u;
     const int wpr = (a.G + 31) / 32;
     if (a.work && !a.ticket) return cudaErrorInvalidValue;   // the work counter is re-armed by the ticket holder
-    if (wpr == 4 && !il_v2()) return launch_flow_field_il(a, grid, st);
+    if (wpr == 4) return launch_flow_field_il(a, grid, st);
     if (a.generate) {
         switch (wpr) {
         case 1: flow_field_warp_kernel<1, true><<<grid, 32, 0, st>>>(a); break;
         case 2: flow_field_warp_kernel<2, true><<<grid, 32, 0, st>>>(a); break;
         case 3: flow_field_warp_kernel<3, true><<<grid, 32, 0, st>>>(a); break;
-        case 4: flow_field_warp_kernel<4, true><<<grid, 32, 0, st>>>(a); break;
         default: return cudaErrorInvalidValue;
         }
     } else {
@@ -741,7 +637,6 @@ cudaError_t launch_flow_field(const FlowArgs &a_in, int grid, cudaStream_t st) {
         case 1: flow_field_warp_kernel<1, false><<<grid, 32, 0, st>>>(a); break;
         case 2: flow_field_warp_kernel<2, false><<<grid, 32, 0, st>>>(a); break;
         case 3: flow_field_warp_kernel<3, false><<<grid, 32, 0, st>>>(a); break;
-        case 4: flow_field_warp_kernel<4, false><<<grid, 32, 0, st>>>(a); break;
         default: return cudaErrorInvalidValue;
         }
     }

@@ -34,7 +34,7 @@ constexpr int IL_NPG = 12;                 // planes of the per-CTA global scrat
 constexpr int IL_PVIS = IL_NPS, IL_PFREE = IL_NPS + 1, IL_NPLX = IL_NPS + 2;
 constexpr int IL_PW = 32 * 4 * 4;          // words of one bit-plane of the padded 128 x 128 grid
 constexpr int IL_STAGE_WORDS = 32 * 32;    // output staging of one pass: 32 rows x 128 bytes
-constexpr int IL_WARPS_PER_SM = 11;        // 20.5 KB of shared memory per warp
+constexpr int IL_WARPS_PER_SM = 10;        // 20.5 KB of shared memory per warp (+ 1 KB per CTA reserved by the driver)
 
 __device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t r;
@@ -137,8 +137,9 @@ __global__ void __launch_bounds__(32, IL_WARPS_PER_SM) flow_field_il_kernel(Flow
             const uint8_t *bytes = reinterpret_cast<const uint8_t *>(pl);
             if (G == 128) {
                 // the lane packs its own rows: chunk (q + lane) % 8 of the row first, so that the eight lanes of a 16-byte
-                // shared-memory phase hit eight different bank groups despite their 512-byte stride
-#pragma unroll
+                // shared-memory phase hit eight different bank groups despite their 512-byte stride.  Rolled over the four
+                // rows (code size); the packed rows are parked in the output staging buffer, which is idle here
+#pragma unroll 1
                 for (int r = 0; r < 4; ++r) {
                     uint32_t o[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -151,8 +152,11 @@ __global__ void __launch_bounds__(32, IL_WARPS_PER_SM) flow_field_il_kernel(Flow
                         for (int w = 0; w < 4; ++w) o[w] = mad_u32(rowops::prmt(z, 0u, 0x4440u + w), sh, o[w]);
                     }
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) A[r][w] = ~o[w];
+                    for (int w = 0; w < 4; ++w) o[w] = ~o[w];
+                    st4(&stage[(r * 32 + lane) * 4], o);
                 }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) ld4(&stage[(r * 32 + lane) * 4], A[r]);
             } else {
                 // 96 < G < 128 (rows are not 16-byte aligned): one byte per lane and one warp vote per word; lane l votes for
                 // column 4l + w, so the vote IS interleaved word w of the row
@@ -320,26 +324,40 @@ __global__ void __launch_bounds__(32, IL_WARPS_PER_SM) flow_field_il_kernel(Flow
         }
 
         // ---- 5. Gray -> binary, in place (plane k becomes cost bit k + 1) ----
-#pragma unroll 1
-        for (int r = 0; r < 4; ++r) {
-            uint32_t acc[4] = {0u, 0u, 0u, 0u};
-#pragma unroll 1
-            for (int k = kmax - 1; k >= IL_NPS; --k) {
-                uint32_t v[4];
-                uint32_t *p = &hi[pidx(k - IL_NPS, r, lane)];
-                ld4(p, v);
+        if (kmax <= 7) {
+            // the common case: at most one plane lives in the L2 scratch, and as the top plane its binary form is itself;
+            // the four rows' requests are issued together
+            uint32_t top[4][4];
 #pragma unroll
-                for (int w = 0; w < 4; ++w) acc[w] ^= v[w];
-                st4(p, acc);
+            for (int r = 0; r < 4; ++r) {
+                top[r][0] = top[r][1] = top[r][2] = top[r][3] = 0u;
+                if (kmax == 7) ld4(&hi[pidx(0, r, lane)], top[r]);
             }
 #pragma unroll
-            for (int k = IL_NPS - 1; k >= 0; --k) {
-                uint32_t v[4];
-                uint32_t *p = &pl[pidx(k, r, lane)];
-                ld4(p, v);
+            for (int r = 0; r < 4; ++r) {
 #pragma unroll
-                for (int w = 0; w < 4; ++w) acc[w] ^= v[w];
-                st4(p, acc);
+                for (int k = IL_NPS - 1; k >= 0; --k) {
+                    uint32_t v[4];
+                    uint32_t *p = &pl[pidx(k, r, lane)];
+                    ld4(p, v);
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) top[r][w] ^= v[w];
+                    st4(p, top[r]);
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int r = 0; r < 4; ++r) {
+                uint32_t acc[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 1
+                for (int k = kmax - 1; k >= 0; --k) {
+                    uint32_t v[4];
+                    uint32_t *p = k < IL_NPS ? &pl[pidx(k, r, lane)] : &hi[pidx(k - IL_NPS, r, lane)];
+                    ld4(p, v);
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) acc[w] ^= v[w];
+                    st4(p, acc);
+                }
             }
         }
         __syncwarp();
@@ -483,7 +501,9 @@ __global__ void __launch_bounds__(32, IL_WARPS_PER_SM) flow_field_il_kernel(Flow
 
 size_t flow_field_il_scratch_words() { return static_cast<size_t>(IL_NPG) * IL_PW; }
 
-int flow_field_il_ctas_per_sm() { return IL_WARPS_PER_SM; }
+// Resident warps per SM of a launch: 8 (2 per scheduler) measured best on 4096-grid batches (profiles/r02a_flow_ab.txt:
+// 0.155 ms against 0.160 ms at 10 and 0.173 ms at 6) — shorter per-grid latency, hence a shorter tail of the launch.
+int flow_field_il_ctas_per_sm() { return 8; }
 
 cudaError_t launch_flow_field_il(const FlowArgs &a, int grid, cudaStream_t st) {
     if (a.generate) flow_field_il_kernel<true><<<grid, 32, 0, st>>>(a);

@@ -11,6 +11,7 @@
 // (neighbour rows from the shared-memory planes), and writes its row of the flow image and of the int32 integration field:
 // one word of the mask is exactly one 128-byte line of cost, so the per-thread 16-byte stores fill whole lines.
 // Algorithmic HBM bytes: 6 B/cell (1 occ read + 4 cost write + 1 flow write).
+#include <mutex>
 #include "flow_bits.cuh"
 
 namespace ffmp {
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
             item = info.item;
         }
         if (item >= count) break;
+        if (a.order) item = static_cast<int>(a.order[item]);
         // ---- 0. item parameters ------------------------------------------------------------------------
         if (tid == 0) {
             const uint32_t env = a.env_idx ? a.env_idx[item] : static_cast<uint32_t>(item);
@@ -451,8 +453,14 @@ cudaError_t launch_flow_field_large(const FlowArgs &a_in, int grid, cudaStream_t
     a.neg1 = 0xFFFFFFFFu;
     a.one = 1u;
     const size_t smem = large_smem_bytes(a.G);
-    static bool configured = false;
-    if (!configured) {
+    // the opt-in belongs to the device (context) of the call: tracked per ordinal (one process may drive several GPUs)
+    static std::mutex mu;
+    static bool configured_dev[64] = {false};
+    int dev = 0;
+    if (cudaError_t ce = cudaGetDevice(&dev); ce != cudaSuccess) return ce;
+    std::lock_guard<std::mutex> lock(mu);
+    const bool known = dev >= 0 && dev < 64;
+    if (!known || !configured_dev[dev]) {
         cudaError_t ce = cudaFuncSetAttribute(flow_field_rows_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(flow_field_rows_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(flow_field_rows_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -460,7 +468,7 @@ cudaError_t launch_flow_field_large(const FlowArgs &a_in, int grid, cudaStream_t
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(flow_field_rows_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(flow_field_rows_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024);
         if (ce != cudaSuccess) return ce;
-        configured = true;
+        if (known) configured_dev[dev] = true;
     }
     if (large_wpr(a.G) == 16) {
         if (a.generate) flow_field_rows_kernel<16, true><<<grid, 512, smem, st>>>(a);

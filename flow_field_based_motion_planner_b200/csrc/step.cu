@@ -10,6 +10,7 @@
 //   rows of loads in flight per thread).  HBM-bound: W^2 read + W^2 written per env-step (+ one more
 //   frame on ring wrap / reset).  Launched with programmatic dependent launch so that its CTAs are
 //   resident and waiting (griddepcontrol.wait) when dynamics_kernel retires.
+#include <mutex>
 #include "ffmp_kernels.cuh"
 
 namespace ffmp {
@@ -708,447 +709,6 @@ __global__ void __launch_bounds__(128) tick_tma_kernel(const __grid_constant__ C
     }
 }
 
-// ---- tick_spec_kernel: tick_tma_kernel with a SPECULATIVE drain (mode 0 only) ----------------------------------
-// The timeline of tick_tma_kernel (profiles/r01b_tick_trace.txt) serialises, after the window has landed, ~1 us of scalar
-// work in warp 0 (footprint test, reward, done, ten global stores) before the four warps start to stream the frame.  Here
-// warp 0 publishes the crop coordinates right after the kinematics; warps 1-3 wait for the window themselves and drain it
-// at once, speculating that the episode continues, while warp 0 does the scalar work and then drains a smaller share.
-// Only when the episode ended (or the ring wraps with a moved robot) a second window is fetched after a barrier and the
-// frame(s) are rewritten.
-struct SpecShared {
-    int ci, cj, pi, pj;        // new / previous robot cell of the speculative frame
-    unsigned int plane;
-    int redo;                  // 1: the episode ended, (ci, cj, plane) now name the first window of the next scenario
-};
-
-__global__ void __launch_bounds__(128, 12) tick_spec_kernel(const __grid_constant__ CUtensorMap tmap, StepArgs a) {
-    extern __shared__ __align__(128) uint8_t tile[];
-    __shared__ __align__(8) uint64_t mbar;
-    __shared__ SpecShared sh;
-    const int e = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int G = a.G, W = a.W;
-    const int wpr = W >> 2;
-    const int tile_w = (W + 15 + 15) & ~15;
-    const int tile_wpr = tile_w >> 2;
-    const int lane = tid & 31, warp = tid >> 5;
-    const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&mbar));
-    const uint32_t tile_s = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
-    const uint32_t bytes = static_cast<uint32_t>(tile_w * W);
-    const int half = W >> 1;
-    const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
-    uint32_t *f_new = reinterpret_cast<uint32_t *>(a.frames + (static_cast<size_t>(e) * a.K + a.slot_new) * W * W);
-    uint32_t *f_old = f_new - (W * W >> 2);
-    // rows [0, split) are drained by warps 1-3 (interleaved), rows [split, W) by warp 0 once its scalar work is done
-    const int split = W - (W >> 3);
-    int rpi = 1, sub = 0, wl = lane;
-    if (wpr <= 32) { rpi = 32 / wpr; sub = lane / wpr; wl = lane - sub * wpr; }
-    auto colmask = [&](int jbase, int w) {
-        uint32_t om = 0;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-            if (static_cast<unsigned>(jbase + 4 * w + c) >= static_cast<unsigned>(G)) om |= 0xFFu << (8 * c);
-        return om;
-    };
-    // this warp's share of one frame out of the staged tile
-    auto drain_share = [&](int ci_, int cj_, bool both, uint32_t *dst, uint32_t *dst2) {
-        const int i0 = ci_ - half, j0 = cj_ - half;
-        const int r0 = warp == 0 ? split : (warp - 1) * rpi, r1 = warp == 0 ? W : split, st = warp == 0 ? rpi : 3 * rpi;
-        if (wpr <= 32) {
-            if (sub < rpi) {
-                const uint32_t om = colmask(j0, wl);
-                if (both) drain_tile<true>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, r0 + sub, st, wl, om, dst, dst2, r1);
-                else drain_tile<false>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, r0 + sub, st, wl, om, dst, nullptr, r1);
-            }
-        } else {
-            for (int w2 = lane; w2 < wpr; w2 += 32) {
-                const uint32_t om = colmask(j0, w2);
-                const int rr0 = warp == 0 ? split : warp - 1, rst = warp == 0 ? 1 : 3;
-                if (both) drain_tile<true>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, rr0, rst, w2, om, dst, dst2, r1);
-                else drain_tile<false>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, rr0, rst, w2, om, dst, nullptr, r1);
-            }
-        }
-    };
-    const bool older = a.write_older != 0;     // ring wrap: every env also rewrites the older frame
-
-    if (warp == 0) {
-        if (lane == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncwarp();
-        uint32_t *st = a.state + static_cast<size_t>(e) * ST_WORDS;
-        const uint4 s0 = *reinterpret_cast<const uint4 *>(st);        // x y yaw gx
-        const uint4 s1 = *reinterpret_cast<const uint4 *>(st + 4);    // gy d_first return steps
-        const float x = __uint_as_float(s0.x), y = __uint_as_float(s0.y), yaw = __uint_as_float(s0.z);
-        const float gx = __uint_as_float(s0.w), gy = __uint_as_float(s1.x);
-        const float d_first = __uint_as_float(s1.y);
-        float ep_return = __uint_as_float(s1.z);
-        int steps = static_cast<int>(s1.w);
-        uint32_t episode = st[ST_EPISODE];
-        long long act = a.actions[e];
-        if (act < 0 || act >= 28) {
-            act = 3;
-            if (lane == 0) atomicOr(a.error_word, 1u);
-        }
-        float v, w, s, c;
-        action_lookup(static_cast<int>(act), v, w);
-        sincos_spec(yaw, s, c);
-        const float nx = fadd(x, fmul(fmul(v, c), a.dt));
-        const float ny = fadd(y, fmul(fmul(v, s), a.dt));
-        const float nyaw = pi_to_pi(fadd(yaw, fmul(w, a.dt)));
-        const int ci = robot_cell(nx), cj = robot_cell(ny);
-        const int pi = robot_cell(x), pj = robot_cell(y);
-        const uint32_t plane = (episode % a.S) * static_cast<uint32_t>(a.N) + static_cast<uint32_t>(e);
-        if (lane == 0) {
-            sh.ci = ci; sh.cj = cj; sh.pi = pi; sh.pj = pj; sh.plane = plane; sh.redo = 0;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-            tma_window(tile_s, &tmap, (cj - half) & ~15, ci - half, static_cast<int>(plane), bar);
-        }
-        __syncthreads();                                   // #1: the crop coordinates are public, the window is on its way
-        // math that does not depend on the map overlaps the copy
-        const float dx = fsub(gx, nx), dy = fsub(gy, ny);
-        const float d = dist_spec(dx, dy);
-        const float bearing = pi_to_pi(fsub(atan2_spec(dy, dx), nyaw));
-        const float vl = dist_spec(fsub(nx, x), fsub(ny, y));
-        const float va = pi_to_pi(fsub(nyaw, yaw));
-        const bool goal = d < 0.5f;
-        mbar_wait_parity(bar, 0);
-        bool hit = false;
-        if (lane < 21) {
-            int di, dj;
-            if (lane < 3) { di = -2; dj = lane - 1; }
-            else if (lane < 18) { di = (lane - 3) / 5 - 1; dj = (lane - 3) % 5 - 2; }
-            else { di = 2; dj = lane - 19; }
-            const int i = ci + di, j = cj + dj;
-            hit = static_cast<unsigned>(i) >= static_cast<unsigned>(G) || static_cast<unsigned>(j) >= static_cast<unsigned>(G);
-            if (!hit) hit = tile[(half + di) * tile_w + ((cj - half) & 15) + half + dj] == 255;
-        }
-        const bool col = __ballot_sync(FULL, hit) != 0;
-        const float r = fadd(fadd(goal ? 1.0f : fmul(0.05f, fsub(d_first, d)), col ? -1.0f : 0.0f), -0.05f);
-        steps += 1;
-        const bool trunc = steps == a.max_steps;
-        const bool done = col || goal || trunc;
-        ep_return = fadd(ep_return, r);
-        if (lane == 0) {
-            a.reward[e] = r;
-            a.done[e] = done ? 1 : 0;
-            a.flags[e] = static_cast<uint8_t>((col ? 1 : 0) | (goal ? 2 : 0) | (trunc ? 4 : 0));
-            *reinterpret_cast<float2 *>(a.term_rel_goal + 2 * e) = make_float2(d, bearing);
-            *reinterpret_cast<float2 *>(a.term_velocity + 2 * e) = make_float2(vl, va);
-        }
-        if (!done) {
-            if (lane == 0) {
-                st[ST_X] = __float_as_uint(nx); st[ST_Y] = __float_as_uint(ny); st[ST_YAW] = __float_as_uint(nyaw);
-                st[ST_RETURN] = __float_as_uint(ep_return);
-                st[ST_STEPS] = static_cast<uint32_t>(steps);
-                *reinterpret_cast<float2 *>(a.rel_goal + 2 * e) = make_float2(d, bearing);
-                *reinterpret_cast<float2 *>(a.velocity + 2 * e) = make_float2(vl, va);
-            }
-            drain_share(ci, cj, older && pi == ci && pj == cj, f_new, f_old);
-        } else {
-            // episode end: begin the next pre-generated scenario; its first window is fetched after barrier #2
-            episode += 1;
-            const uint32_t *rec = a.scen + (static_cast<size_t>(episode % a.S) * a.N + e) * SC_WORDS;
-            const uint4 r0 = *reinterpret_cast<const uint4 *>(rec);
-            const float sx = __uint_as_float(r0.x), sy = __uint_as_float(r0.y), syaw = __uint_as_float(r0.z);
-            const float ngx = __uint_as_float(r0.w), ngy = __uint_as_float(rec[SC_GY]);
-            const float ndx = fsub(ngx, sx), ndy = fsub(ngy, sy);
-            const float nd = dist_spec(ndx, ndy);
-            const float nbearing = pi_to_pi(fsub(atan2_spec(ndy, ndx), syaw));
-            if (lane == 0) {
-                a.fin_return[e] = ep_return;
-                a.fin_length[e] = steps;
-                const uint32_t idx = atomicAdd(a.regen_count, 1u);
-                a.regen_env[idx] = static_cast<uint32_t>(e);
-                a.regen_episode[idx] = episode + static_cast<uint32_t>(a.S) - 1u;
-                *reinterpret_cast<uint4 *>(st) = make_uint4(__float_as_uint(sx), __float_as_uint(sy), __float_as_uint(syaw), __float_as_uint(ngx));
-                *reinterpret_cast<uint4 *>(st + 4) = make_uint4(__float_as_uint(ngy), __float_as_uint(nd), __float_as_uint(0.0f), 0u);
-                st[ST_EPISODE] = episode;
-                *reinterpret_cast<float2 *>(a.rel_goal + 2 * e) = make_float2(nd, nbearing);
-                *reinterpret_cast<float2 *>(a.velocity + 2 * e) = make_float2(0.0f, 0.0f);
-                sh.ci = robot_cell(sx); sh.cj = robot_cell(sy);
-                sh.plane = (episode % a.S) * static_cast<uint32_t>(a.N) + static_cast<uint32_t>(e);
-                sh.redo = 1;
-            }
-        }
-    } else {
-        __syncthreads();                                   // #1
-        const int ci = sh.ci, cj = sh.cj, pi = sh.pi, pj = sh.pj;
-        mbar_wait_parity(bar, 0);
-        drain_share(ci, cj, older && pi == ci && pj == cj, f_new, f_old);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of `tile` precede a possible async overwrite
-    __syncthreads();                                       // #2: the verdict of warp 0 is public
-    const int redo = sh.redo;
-    const int ci = sh.ci, cj = sh.cj, pi = sh.pi, pj = sh.pj;
-    if (redo) {
-        // first observation of the new episode: both frames are the window at the start pose
-        if (tid == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-            tma_window(tile_s, &tmap, (cj - half) & ~15, ci - half, static_cast<int>(sh.plane), bar);
-        }
-        mbar_wait_parity(bar, 1);
-        drain_share(ci, cj, true, f_new, f_old);
-    } else if (older && !(pi == ci && pj == cj)) {
-        // ring wrap of a continuing env that moved: the older frame is the window at the previous pose
-        if (tid == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-            tma_window(tile_s, &tmap, (pj - half) & ~15, pi - half, static_cast<int>(sh.plane), bar);
-        }
-        mbar_wait_parity(bar, 1);
-        drain_share(pi, pj, false, f_old, nullptr);
-    }
-}
-
-// ---- tick_pipe_kernel: the env step as a persistent producer / consumer pipeline ---------------------------------
-// The per-CTA timeline of tick_tma_kernel (profiles/r01b_tick_trace.txt) is a 4.5-5.5 us dependent chain (state load ->
-// kinematics -> window TMA -> footprint -> drain) with one window in flight per CTA, i.e. ~12 windows per SM: not enough
-// bytes in flight to cover the latency.  Here two persistent CTAs per SM each own ~14 envs:
-//   * warp 0 (producer) runs the scalar part of the step ONE LANE PER ENV (state + action -> kinematics, relative goal,
-//     velocity), parks the results in shared memory and issues the window TMA of every env back to back into a ring of
-//     PIPE_NS tile slots (full / empty mbarriers), so up to 2 * PIPE_NS windows per SM are in flight at any time;
-//   * warps 1..PIPE_NC (consumers) take the windows as they land: footprint collision test from the staged tile,
-//     reward / done / auto-reset (second TMA through a private barrier in the rare episode end), then stream the frame to
-//     the ring with coalesced stores and hand the slot back.
-struct EnvMeta {
-    float nx, ny, nyaw;          // pose after the move
-    float d, bearing, vl, va;    // relative goal and velocity after the move
-    float d_first, ep_return;    // episode latches (before this step's reward)
-    int steps;                   // after the increment
-    int ci, cj, pi, pj;          // new / previous robot cell
-    uint32_t episode;
-    uint32_t goal;               // d < GOAL_TH
-};
-static_assert(sizeof(EnvMeta) == 64, "EnvMeta is read as four 16-byte words");
-
-constexpr int PIPE_NS = 6;   // window slots per CTA
-constexpr int PIPE_NC = 6;   // consumer warps per CTA
-// Every slot is drained by one fixed warp (slot = j % NS, warp = j % NC): a consumer that waits for round r of a slot has
-// itself consumed round r-1, so the parity wait can never be satisfied by an older phase.
-static_assert(PIPE_NS % PIPE_NC == 0, "a slot must always be drained by the same consumer warp");
-
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
-__global__ void __launch_bounds__(32 * (1 + PIPE_NC)) tick_pipe_kernel(const __grid_constant__ CUtensorMap tmap, StepArgs a) {
-    extern __shared__ __align__(128) uint8_t tiles[];
-    __shared__ __align__(16) EnvMeta meta[32];
-    __shared__ __align__(8) uint64_t full[PIPE_NS], empty[PIPE_NS], aux[PIPE_NC];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = a.G, W = a.W;
-    const int wpr = W >> 2;
-    const int tile_w = (W + 15 + 15) & ~15;
-    const int tile_wpr = tile_w >> 2;
-    const int half = W >> 1;
-    const uint32_t bytes = static_cast<uint32_t>(tile_w * W);
-    const uint32_t tile_stride = (bytes + 127u) & ~127u;
-    const int first = blockIdx.x, stride = gridDim.x;
-    const int n_local = first < a.N ? (a.N - first + stride - 1) / stride : 0;     // <= 32 (launch_step sizes the grid)
-    const uint32_t tiles_s = static_cast<uint32_t>(__cvta_generic_to_shared(tiles));
-    auto bar_addr = [](uint64_t *b) { return static_cast<uint32_t>(__cvta_generic_to_shared(b)); };
-
-    if (tid == 0) {
-        for (int s = 0; s < PIPE_NS; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr(&full[s])) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr(&empty[s])) : "memory");
-        }
-        for (int c = 0; c < PIPE_NC; ++c)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr(&aux[c])) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (warp == 0) {
-        // ================= producer: one lane per env =================
-        const int e = first + lane * stride;
-        int ci = 0, cj = 0;
-        uint32_t plane = 0;
-        if (lane < n_local) {
-            const uint32_t *st = a.state + static_cast<size_t>(e) * ST_WORDS;
-            const uint4 s0 = *reinterpret_cast<const uint4 *>(st);        // x y yaw gx
-            const uint4 s1 = *reinterpret_cast<const uint4 *>(st + 4);    // gy d_first return steps
-            const float x = __uint_as_float(s0.x), y = __uint_as_float(s0.y), yaw = __uint_as_float(s0.z);
-            const float gx = __uint_as_float(s0.w), gy = __uint_as_float(s1.x);
-            const uint32_t episode = st[ST_EPISODE];
-            long long act = a.actions[e];
-            if (act < 0 || act >= 28) {
-                act = 3;
-                atomicOr(a.error_word, 1u);
-            }
-            float v, w, s, c;
-            action_lookup(static_cast<int>(act), v, w);
-            sincos_spec(yaw, s, c);
-            const float nx = fadd(x, fmul(fmul(v, c), a.dt));
-            const float ny = fadd(y, fmul(fmul(v, s), a.dt));
-            const float nyaw = pi_to_pi(fadd(yaw, fmul(w, a.dt)));
-            ci = robot_cell(nx);
-            cj = robot_cell(ny);
-            plane = (episode % a.S) * static_cast<uint32_t>(a.N) + static_cast<uint32_t>(e);
-            const float dx = fsub(gx, nx), dy = fsub(gy, ny);
-            EnvMeta m;
-            m.nx = nx; m.ny = ny; m.nyaw = nyaw;
-            m.d = dist_spec(dx, dy);
-            m.bearing = pi_to_pi(fsub(atan2_spec(dy, dx), nyaw));
-            m.vl = dist_spec(fsub(nx, x), fsub(ny, y));
-            m.va = pi_to_pi(fsub(nyaw, yaw));
-            m.d_first = __uint_as_float(s1.y);
-            m.ep_return = __uint_as_float(s1.z);
-            m.steps = static_cast<int>(s1.w) + 1;
-            m.ci = ci; m.cj = cj; m.pi = robot_cell(x); m.pj = robot_cell(y);
-            m.episode = episode;
-            m.goal = m.d < 0.5f ? 1u : 0u;
-            meta[lane] = m;
-        }
-        __syncwarp();
-        // window fetches as slots become free (speculating that the episode continues).  The lanes run this concurrently
-        // (no order between lanes exists), so a lane of round r waits for EVERY earlier phase of its slot's empty barrier in
-        // turn: a single parity wait could be satisfied by an older phase.
-        if (lane < n_local) {
-            const int slot = lane % PIPE_NS, round = lane / PIPE_NS;
-            for (int rr = 0; rr < round; ++rr) mbar_wait_parity(bar_addr(&empty[slot]), static_cast<uint32_t>(rr & 1));
-            const uint32_t fb = bar_addr(&full[slot]);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(bytes) : "memory");
-            tma_window(tiles_s + slot * tile_stride, &tmap, (cj - half) & ~15, ci - half, static_cast<int>(plane), fb);
-        }
-        return;
-    }
-
-    // ================= consumers: one warp per window =================
-    const int c = warp - 1;
-    const uint32_t ab = bar_addr(&aux[c]);
-    uint32_t aux_phase = 0;
-    int rpi = 1, sub = 0, wl = lane;
-    if (wpr <= 32) { rpi = 32 / wpr; sub = lane / wpr; wl = lane - sub * wpr; }
-    auto colmask = [&](int jbase, int w) {
-        uint32_t om = 0;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
-            if (static_cast<unsigned>(jbase + 4 * w + cc) >= static_cast<unsigned>(G)) om |= 0xFFu << (8 * cc);
-        return om;
-    };
-    // footprint cell of this lane (ffmp.py:85-105: 21 offsets with di^2 + dj^2 <= 6), from the lane index
-    int fdi, fdj;
-    if (lane < 3) { fdi = -2; fdj = lane - 1; }
-    else if (lane < 18) { fdi = (lane - 3) / 5 - 1; fdj = (lane - 3) % 5 - 2; }
-    else { fdi = 2; fdj = lane - 19; }
-
-    for (int j = c; j < n_local; j += PIPE_NC) {
-        const int e = first + j * stride;
-        const int slot = j % PIPE_NS;
-        const uint8_t *tile = tiles + slot * tile_stride;
-        const uint32_t tile_s = tiles_s + slot * tile_stride;
-        const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
-        mbar_wait_parity(bar_addr(&full[slot]), static_cast<uint32_t>((j / PIPE_NS) & 1));
-        const EnvMeta m = meta[j];
-        int ci = m.ci, cj = m.cj, pi = m.pi, pj = m.pj;
-        uint32_t episode = m.episode;
-        // ---- collision from the staged window (the 21 footprint cells sit at its centre) ----
-        bool hit = false;
-        if (lane < 21) {
-            const int i = ci + fdi, jj = cj + fdj;
-            hit = static_cast<unsigned>(i) >= static_cast<unsigned>(G) || static_cast<unsigned>(jj) >= static_cast<unsigned>(G);
-            if (!hit) hit = tile[(half + fdi) * tile_w + ((cj - half) & 15) + half + fdj] == 255;
-        }
-        const bool col = __ballot_sync(FULL, hit) != 0;
-        const bool goal = m.goal != 0;
-        const float r = fadd(fadd(goal ? 1.0f : fmul(0.05f, fsub(m.d_first, m.d)), col ? -1.0f : 0.0f), -0.05f);
-        const bool trunc = m.steps == a.max_steps;
-        const bool done = col || goal || trunc;
-        const float ep_return = fadd(m.ep_return, r);
-        uint32_t *st = a.state + static_cast<size_t>(e) * ST_WORDS;
-        if (lane == 0) {
-            a.reward[e] = r;
-            a.done[e] = done ? 1 : 0;
-            a.flags[e] = static_cast<uint8_t>((col ? 1 : 0) | (goal ? 2 : 0) | (trunc ? 4 : 0));
-            *reinterpret_cast<float2 *>(a.term_rel_goal + 2 * e) = make_float2(m.d, m.bearing);
-            *reinterpret_cast<float2 *>(a.term_velocity + 2 * e) = make_float2(m.vl, m.va);
-        }
-        bool two = a.write_older != 0;
-        if (done) {
-            // episode end: begin the next pre-generated scenario and fetch its first window into the same slot
-            episode += 1;
-            const uint32_t *rec = a.scen + (static_cast<size_t>(episode % a.S) * a.N + e) * SC_WORDS;
-            const uint4 r0 = *reinterpret_cast<const uint4 *>(rec);
-            const float x = __uint_as_float(r0.x), y = __uint_as_float(r0.y), yaw = __uint_as_float(r0.z);
-            const float ngx = __uint_as_float(r0.w), ngy = __uint_as_float(rec[SC_GY]);
-            ci = pi = robot_cell(x);
-            cj = pj = robot_cell(y);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // footprint reads of the tile precede the overwrite
-            __syncwarp();
-            if (lane == 0) {
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ab), "r"(bytes) : "memory");
-                tma_window(tile_s, &tmap, (cj - half) & ~15, ci - half, static_cast<int>((episode % a.S) * a.N + e), ab);
-            }
-            const float dx = fsub(ngx, x), dy = fsub(ngy, y);
-            const float d = dist_spec(dx, dy);
-            const float bearing = pi_to_pi(fsub(atan2_spec(dy, dx), yaw));
-            if (lane == 0) {
-                a.fin_return[e] = ep_return;
-                a.fin_length[e] = m.steps;
-                const uint32_t idx = atomicAdd(a.regen_count, 1u);
-                a.regen_env[idx] = static_cast<uint32_t>(e);
-                a.regen_episode[idx] = episode + static_cast<uint32_t>(a.S) - 1u;
-                *reinterpret_cast<uint4 *>(st) = make_uint4(__float_as_uint(x), __float_as_uint(y), __float_as_uint(yaw), __float_as_uint(ngx));
-                *reinterpret_cast<uint4 *>(st + 4) = make_uint4(__float_as_uint(ngy), __float_as_uint(d), __float_as_uint(0.0f), 0u);
-                st[ST_EPISODE] = episode;
-                *reinterpret_cast<float2 *>(a.rel_goal + 2 * e) = make_float2(d, bearing);
-                *reinterpret_cast<float2 *>(a.velocity + 2 * e) = make_float2(0.0f, 0.0f);
-            }
-            mbar_wait_parity(ab, aux_phase);
-            aux_phase ^= 1u;
-            two = true;
-        } else if (lane == 0) {
-            st[ST_X] = __float_as_uint(m.nx); st[ST_Y] = __float_as_uint(m.ny); st[ST_YAW] = __float_as_uint(m.nyaw);
-            st[ST_RETURN] = __float_as_uint(ep_return);
-            st[ST_STEPS] = static_cast<uint32_t>(m.steps);
-            *reinterpret_cast<float2 *>(a.rel_goal + 2 * e) = make_float2(m.d, m.bearing);
-            *reinterpret_cast<float2 *>(a.velocity + 2 * e) = make_float2(m.vl, m.va);
-        }
-        // ---- stream the window to the frame ring ----
-        const bool same = pi == ci && pj == cj;
-        const int i0 = ci - half, j0 = cj - half;
-        uint32_t *f_new = reinterpret_cast<uint32_t *>(a.frames + (static_cast<size_t>(e) * a.K + a.slot_new) * W * W);
-        uint32_t *f_old = f_new - (W * W >> 2);
-        if (wpr <= 32) {
-            if (sub < rpi) {
-                const uint32_t om = colmask(j0, wl);
-                if (two && same) drain_tile<true>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, sub, rpi, wl, om, f_new, f_old);
-                else drain_tile<false>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, sub, rpi, wl, om, f_new, nullptr);
-            }
-        } else {
-            for (int w2 = lane; w2 < wpr; w2 += 32) {
-                const uint32_t om = colmask(j0, w2);
-                if (two && same) drain_tile<true>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, 0, 1, w2, om, f_new, f_old);
-                else drain_tile<false>(tile32, tile_wpr, G, W, wpr, i0, j0 & 15, 0, 1, w2, om, f_new, nullptr);
-            }
-        }
-        if (two && !same) {
-            // ring wrap of a continuing env: the older frame is the window at the previous pose
-            const int p0 = pi - half, q0 = pj - half;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ab), "r"(bytes) : "memory");
-                tma_window(tile_s, &tmap, q0 & ~15, p0, static_cast<int>((episode % a.S) * a.N + e), ab);
-            }
-            mbar_wait_parity(ab, aux_phase);
-            aux_phase ^= 1u;
-            if (wpr <= 32) {
-                if (sub < rpi) drain_tile<false>(tile32, tile_wpr, G, W, wpr, p0, q0 & 15, sub, rpi, wl, colmask(q0, wl), f_old, nullptr);
-            } else {
-                for (int w2 = lane; w2 < wpr; w2 += 32)
-                    drain_tile<false>(tile32, tile_wpr, G, W, wpr, p0, q0 & 15, 0, 1, w2, colmask(q0, w2), f_old, nullptr);
-            }
-        }
-        // hand the slot back: the generic reads above are ordered before the producer's next async write
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_addr(&empty[slot]));
-    }
-}
-
 // Batched FFMP.rewarder / rewarder2 / reward_calculator (ffmp.py:130-188): one warp per item.
 __global__ void __launch_bounds__(128) rewarder_kernel(RewarderArgs a) {
     const int item = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -1183,44 +743,34 @@ __global__ void __launch_bounds__(128) rewarder_kernel(RewarderArgs a) {
 
 }  // namespace
 
-cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t st, cudaEvent_t between, bool fused, bool pipe,
-                        bool spec) {
+// Dynamic shared memory above 48 KB needs a per-function opt-in, and the attribute belongs to the device (context) the call
+// is made on: one process may drive several GPUs through the C-ABI, so the opt-in is tracked per device ordinal.
+static cudaError_t opt_in_shared(size_t smem) {
+    static std::mutex mu;
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce != cudaSuccess) return ce;
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && smem <= configured[dev]) return cudaSuccess;
+    ce = cudaFuncSetAttribute(tick_tma_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (ce == cudaSuccess)
+        ce = cudaFuncSetAttribute(tick_tma_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (ce == cudaSuccess)
+        ce = cudaFuncSetAttribute(observe_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (ce == cudaSuccess && dev >= 0 && dev < 64) configured[dev] = smem;
+    return ce;
+}
+
+cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t st, cudaEvent_t between, bool fused) {
     if (a.N <= 0) return cudaSuccess;
     const size_t smem = tmap ? static_cast<size_t>((a.W + 30) & ~15) * a.W + 16 : 0;
     if (tmap) {
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
-            cudaError_t ce = cudaFuncSetAttribute(tick_tma_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-            if (ce == cudaSuccess)
-                ce = cudaFuncSetAttribute(tick_tma_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-            if (ce == cudaSuccess)
-                ce = cudaFuncSetAttribute(tick_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-            if (ce == cudaSuccess)
-                ce = cudaFuncSetAttribute(observe_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (smem > 48 * 1024) {
+            const cudaError_t ce = opt_in_shared(smem);
             if (ce != cudaSuccess) return ce;
-            configured = smem;
         }
         if (fused && !between) {
-            if (a.mode == 0 && spec && !pipe && !a.trace) {
-                tick_spec_kernel<<<a.N, 128, smem, st>>>(*tmap, a);
-                return cudaGetLastError();
-            }
-            if (a.mode == 0 && pipe) {
-                // persistent producer / consumer pipeline: two CTAs per SM, at most 32 envs per CTA
-                const size_t tile_stride = (smem - 16 + 127) & ~static_cast<size_t>(127);
-                const size_t psmem = PIPE_NS * tile_stride;
-                static size_t pipe_configured = 0;
-                if (psmem > pipe_configured) {
-                    cudaError_t ce = cudaFuncSetAttribute(tick_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(psmem));
-                    if (ce != cudaSuccess) return ce;
-                    pipe_configured = psmem;
-                }
-                int grid = 2 * 148;
-                if ((a.N + 31) / 32 > grid) grid = (a.N + 31) / 32;
-                if (grid > a.N) grid = a.N;
-                tick_pipe_kernel<<<grid, 32 * (1 + PIPE_NC), psmem, st>>>(*tmap, a);
-                return cudaGetLastError();
-            }
             if (a.trace) tick_tma_kernel<true, 0><<<a.N, 128, smem, st>>>(*tmap, a);
             else if (a.W == 100) tick_tma_kernel<false, 100><<<a.N, 128, smem, st>>>(*tmap, a);   // the reference's window
             else if (a.W == 64) tick_tma_kernel<false, 64><<<a.N, 128, smem, st>>>(*tmap, a);     // BASELINE config 2

@@ -41,29 +41,48 @@ def generate_scenarios(env_gids, episodes, grid, p_occ=0.10, goal_mode=0, block_
     return occ, scen
 
 
-def flow_field(occ, goal_cells, want_cost=True):
-    """occ u8[n,G,G] (non-zero = occupied), goal_cells int[n,2] -> (cost i32[n,G,G] | None, flow u8[n,G,G])."""
+def flow_field(occ, goal_cells, want_cost=True, out=None, workspace=None):
+    """occ u8[n,G,G] (non-zero = occupied), goal_cells int[n,2] -> (cost i32[n,G,G] | None, flow u8[n,G,G]).
+
+    out = (cost, flow) and workspace (u8, flow_field_workspace(n, G) bytes) may be passed to reuse buffers between calls."""
     L = native.lib()
     dev = _dev_index(occ)
     assert occ.dtype == torch.uint8 and occ.dim() == 3 and occ.shape[1] == occ.shape[2]
     occ = occ.contiguous()
     n, G = occ.shape[0], occ.shape[1]
-    goals = goal_cells.to(device=occ.device, dtype=torch.int32).contiguous()
+    goals = goal_cells
+    if goals.dtype != torch.int32 or goals.device != occ.device or not goals.is_contiguous():
+        goals = goal_cells.to(device=occ.device, dtype=torch.int32).contiguous()
     need_cost = want_cost
-    cost = torch.empty((n, G, G), dtype=torch.int32, device=occ.device) if need_cost else None
-    flow = torch.empty((n, G, G), dtype=torch.uint8, device=occ.device)
+    if out is not None:
+        cost, flow = out
+        assert flow.dtype == torch.uint8 and flow.shape == occ.shape and flow.is_contiguous() and flow.device == occ.device
+        if need_cost:
+            assert cost.dtype == torch.int32 and cost.shape == occ.shape and cost.is_contiguous() and cost.device == occ.device
+    else:
+        cost = torch.empty((n, G, G), dtype=torch.int32, device=occ.device) if need_cost else None
+        flow = torch.empty((n, G, G), dtype=torch.uint8, device=occ.device)
     if n == 0:
         return cost, flow
     ws_bytes = L.ffmp_op_flow_field_workspace(n, G)
     if n > 0 and ws_bytes == 0:
         raise native.NativeError(f"flow_field: grid {G} is not supported by this build")
-    ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=occ.device)
+    ws = workspace
+    if ws is None:
+        ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=occ.device)
+    assert ws.dtype == torch.uint8 and ws.numel() >= ws_bytes and ws.device == occ.device
     with torch.cuda.device(occ.device):
         native.check(L.ffmp_op_flow_field(dev, n, G, C.c_void_p(occ.data_ptr()), C.c_void_p(goals.data_ptr()),
                                           C.c_void_p(cost.data_ptr()) if need_cost else None,
                                           C.c_void_p(flow.data_ptr()), C.c_void_p(ws.data_ptr()), _stream(occ.device)),
                      "ffmp_op_flow_field")
     return (cost if want_cost else None), flow
+
+
+def flow_field_workspace(n, grid, device):
+    """A workspace tensor for flow_field(..., workspace=) on n grids of side `grid`."""
+    size = native.lib().ffmp_op_flow_field_workspace(n, grid)
+    return torch.empty((max(size, 16),), dtype=torch.uint8, device=device)
 
 
 def scan(grid_map, pose, beams=360, range_max=3.5, flow_mode=True):

@@ -432,14 +432,6 @@ def test_env_collision_equals_reference_is_collision_on_crop(ffmp, cuda_device):
 # ---------------------------------------------------------------------------------------------------
 # kernel variants behind environment switches (read by the library at create / launch time)
 # ---------------------------------------------------------------------------------------------------
-def test_rollout_pipe_kernel_variant(ffmp, monkeypatch):
-    """FFMP_TICK_PIPE=1: the persistent producer/consumer tick kernel.  4096 envs put 14 envs on every CTA, i.e. three
-    rounds through the 6-slot window ring (the empty-barrier protocol), 16 steps cross a frame-ring wrap."""
-    monkeypatch.setenv("FFMP_TICK_PIPE", "1")
-    rollout_parity(ffmp, 4096, 16, seed=5, grid=128, window=100, check_every=4)
-    rollout_parity(ffmp, 40, 300, seed=6, grid=64, window=32, max_steps=15, check_every=50)
-
-
 @pytest.mark.parametrize("G", [32, 64, 128])
 def test_flow_field_rows_kernel_on_small_grids(ffmp, cuda_device, G, monkeypatch):
     """FFMP_FLOW_ROWS=1: the CTA-per-grid / thread-per-row kernel of the large-map path, on grids the warp kernel normally
