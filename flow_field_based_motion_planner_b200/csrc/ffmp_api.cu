@@ -148,6 +148,8 @@ struct ffmp_handle {
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double acc8 = 0;
     uint64_t acc_n = 0;
+    uint8_t *term_frames = nullptr;        // caller's [N][2][W][W] buffer (ffmp_set_terminal_obs) or null
+    int32_t *term_order = nullptr;         // library-owned [N][8] (allocated with the first ffmp_set_terminal_obs)
     unsigned long long *trace = nullptr;   // FFMP_TRACE=1: [N][8] tick-kernel timestamps (library-owned, diagnostics only)
 
     uint32_t *error_word() const { return reinterpret_cast<uint32_t *>(static_cast<char *>(b.workspace) + ws.error_word); }
@@ -190,6 +192,8 @@ ffmp::StepArgs step_args(const ffmp_handle *h) {
     a.error_word = h->error_word();
     a.obs_order = h->obs_order();
     a.trace = h->trace;
+    a.term_frames = h->term_frames;
+    a.term_order = h->term_frames ? h->term_order : nullptr;
     return a;
 }
 
@@ -230,6 +234,11 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
     }
     if (tev) CK(cudaEventRecord(tev[1], st));
     h->launches += one_kernel ? 1 : 2;
+    if (mode == 0 && a.term_frames) {
+        // the terminal observations of the envs that finished, before their slot is handed to the regeneration
+        CK(ffmp::launch_terminal_obs(a, st));
+        h->launches += 1;
+    }
     CK(cudaEventRecord(h->ev_step[l], st));
     CK(cudaStreamWaitEvent(h->side[l], h->ev_step[l], 0));
     if (tev) CK(cudaEventRecord(tev[2], h->side[l]));
@@ -386,6 +395,7 @@ int ffmp_destroy(ffmp_handle *h) {
                      h->acc[4] / n, h->acc[5] / n);
     }
     if (h->trace) cudaFree(h->trace);
+    if (h->term_order) cudaFree(h->term_order);
     if (h->flag_host) cudaFreeHost(const_cast<uint32_t *>(h->flag_host));
     if (h->tev[0][0])
         for (int i = 0; i < ffmp_handle::TIMING_RING; ++i)
@@ -614,6 +624,16 @@ int ffmp_debug_trace(ffmp_handle *h, uint64_t *out_host, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaMemcpyAsync(out_host, h->trace, static_cast<size_t>(h->cfg.num_envs) * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return FFMP_OK;
+}
+
+int ffmp_set_terminal_obs(ffmp_handle *h, uint8_t *term_frames_dev) {
+    if (!h) return fail(FFMP_ERR_ARG, "handle is null");
+    if (h->wait_mode) return fail(FFMP_ERR_STATE, "a host-buffer step is pending");
+    DeviceGuard guard(h->cfg.device);
+    if (term_frames_dev && !h->term_order)
+        CK(cudaMalloc(&h->term_order, static_cast<size_t>(h->cfg.num_envs) * 8 * sizeof(int32_t)));
+    h->term_frames = term_frames_dev;
     return FFMP_OK;
 }
 

@@ -66,6 +66,8 @@ struct StepArgs {
     int32_t *fin_length;
     uint32_t *regen_env, *regen_episode, *regen_count;  // regeneration request list
     uint32_t *obs_order;        // [N][8] crop orders, dynamics_kernel -> observe_kernel
+    int32_t *term_order;        // [N][8] or null: (ci, cj, pi, pj, plane) of the envs that finished, step kernel -> terminal_obs_kernel
+    uint8_t *term_frames;       // [N][2][W][W] or null: terminal local_map of the envs that finished in this step
     uint32_t *error_word;
     unsigned long long *trace;  // optional [N][8] per-CTA timestamps of the tick kernel (diagnostics, FFMP_TRACE=1) or null
 };
@@ -143,6 +145,7 @@ cudaError_t launch_flow_order(const int32_t *goal_cells, int n, int G, uint32_t 
 cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t st, cudaEvent_t between = nullptr,
                         bool fused = true);
 cudaError_t launch_rewarder(const RewarderArgs &a, cudaStream_t st);
+cudaError_t launch_terminal_obs(const StepArgs &a, cudaStream_t st);      // step.cu: behind a mode-0 step when term_frames is set
 int flow_field_max_grid(int G);            // resident CTAs for a full wave (multiple of the SM count)
 size_t flow_field_scratch_words(int G);    // hi_scratch words per CTA
 bool flow_field_supported(int G);

@@ -51,6 +51,14 @@ __device__ __forceinline__ ColPlan make_plan(int G, int j0) {
 
 // The per-env scalar step (SPEC.md §7).  WARP = false: one thread per env.  WARP = true: a whole warp runs it
 // redundantly for one env (lanes 0..20 take one footprint cell each, lane 0 does the writes); every lane
+// terminal observation order of an env that finished (SPEC.md §7): the crop centres of [previous frame, terminal frame] on the
+// finished episode's plane; terminal_obs_kernel turns it into info["terminal_local_map"] before the slot is regenerated
+__device__ __forceinline__ void store_term_order(const StepArgs &a, int e, int ci, int cj, int pi, int pj, uint32_t episode) {
+    int32_t *o = a.term_order + static_cast<size_t>(e) * 8;
+    *reinterpret_cast<int4 *>(o) = make_int4(ci, cj, pi, pj);
+    o[4] = static_cast<int32_t>((episode % a.S) * static_cast<uint32_t>(a.N) + static_cast<uint32_t>(e));
+}
+
 // returns the same crop order.  o0 = (ci, cj, pi, pj), o1 = (plane, flags: bit0 active, bit1 two frames).
 template <bool WARP>
 __device__ __forceinline__ void dynamics_env(const StepArgs &a, int e, int lane, uint4 &o0, uint2 &o1) {
@@ -125,7 +133,10 @@ __device__ __forceinline__ void dynamics_env(const StepArgs &a, int e, int lane,
             *reinterpret_cast<float2 *>(a.term_velocity + 2 * e) = make_float2(vl, va);
         }
         if (done) {
-            if (lead) { a.fin_return[e] = ep_return; a.fin_length[e] = steps; }
+            if (lead) {
+                a.fin_return[e] = ep_return; a.fin_length[e] = steps;
+                if (a.term_order) store_term_order(a, e, ci, cj, robot_cell(x), robot_cell(y), episode);
+            }
             begin = true;
         } else {
             pi = robot_cell(x);
@@ -584,7 +595,10 @@ __global__ void __launch_bounds__(128) tick_tma_kernel(const __grid_constant__ C
                 *reinterpret_cast<float2 *>(a.term_velocity + 2 * e) = make_float2(vl, va);
             }
             if (done) {
-                if (lane == 0) { a.fin_return[e] = ep_return; a.fin_length[e] = steps; }
+                if (lane == 0) {
+                    a.fin_return[e] = ep_return; a.fin_length[e] = steps;
+                    if (a.term_order) store_term_order(a, e, ci, cj, robot_cell(x), robot_cell(y), episode);
+                }
                 begin = true;
                 parity = 1;   // the window of the next scenario arrives in the barrier's second phase
             } else {
@@ -798,6 +812,33 @@ cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t
     cfg.dynamicSmemBytes = smem;
     if (tmap) return cudaLaunchKernelEx(&cfg, observe_tma_kernel<false>, *tmap, a);
     return cudaLaunchKernelEx(&cfg, observe_kernel, a);
+}
+
+// info["terminal_local_map"] (SPEC.md §7, a15; the reference's last tick of an episode, train.py:611-664): one CTA per env,
+// envs that did not finish exit at once (~2.5 % finish per step in the bench workload).  Runs on the step's stream before the
+// finished slot's regeneration is released, so the finished episode's flow image is still intact.
+__global__ void __launch_bounds__(128) terminal_obs_kernel(StepArgs a) {
+    const int e = blockIdx.x;
+    if (a.done[e] == 0) return;
+    const int G = a.G, W = a.W, half = W >> 1;
+    const int32_t *o = a.term_order + static_cast<size_t>(e) * 8;
+    const uint8_t *img = a.flow + static_cast<size_t>(static_cast<uint32_t>(o[4])) * G * G;
+    uint8_t *dst = a.term_frames + static_cast<size_t>(e) * 2 * W * W;
+    for (int f = 0; f < 2; ++f) {
+        const int i0 = (f == 0 ? o[2] : o[0]) - half, j0 = (f == 0 ? o[3] : o[1]) - half;
+        for (int k = threadIdx.x; k < W * W; k += blockDim.x) {
+            const int r = k / W, c = k - r * W;
+            const int i = i0 + r, j = j0 + c;
+            const bool in = static_cast<unsigned>(i) < static_cast<unsigned>(G) && static_cast<unsigned>(j) < static_cast<unsigned>(G);
+            dst[static_cast<size_t>(f) * W * W + k] = in ? __ldg(img + static_cast<size_t>(i) * G + j) : static_cast<uint8_t>(255);
+        }
+    }
+}
+
+cudaError_t launch_terminal_obs(const StepArgs &a, cudaStream_t st) {
+    if (a.N <= 0 || !a.term_frames || !a.term_order) return cudaSuccess;
+    terminal_obs_kernel<<<a.N, 128, 0, st>>>(a);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_rewarder(const RewarderArgs &a, cudaStream_t st) {

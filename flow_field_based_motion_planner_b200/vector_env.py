@@ -47,6 +47,7 @@ class FFMPConfig:
     seed: int = 0
     env_id_base: int = 0
     dt: float = 0.1
+    terminal_obs: bool = False      # also keep the terminal local_map of finished envs (info["terminal_local_map"])
     device: str = "cuda:0"
 
 
@@ -129,6 +130,12 @@ class FFMPVectorEnv:
                                "done", "flags", "term_rel_goal", "term_velocity", "fin_return", "fin_length")},
                            workspace=self._workspace.data_ptr())
         native.check(self._L.ffmp_bind(self._h, C.byref(b)), "ffmp_bind")
+        self.term_local_map = None
+        if cfg.terminal_obs:
+            # rows of envs that did not finish keep their last terminal observation (train.py:611-664 reads it on `done` only)
+            with torch.cuda.device(d):
+                self.term_local_map = torch.zeros((N, 2, W, W), dtype=torch.uint8, device=d)
+            native.check(self._L.ffmp_set_terminal_obs(self._h, C.c_void_p(self.term_local_map.data_ptr())), "ffmp_set_terminal_obs")
         self._done_bool = self.done.view(torch.bool)
         self._views = {}
         self._host_out = {}
@@ -189,9 +196,12 @@ class FFMPVectorEnv:
         return self._obs(), self.reward, self._done_bool, self._info()
 
     def _info(self):
-        return {"flags": self.flags, "terminal_relative_goal": self.term_rel_goal,
+        info = {"flags": self.flags, "terminal_relative_goal": self.term_rel_goal,
                 "terminal_velocity": self.term_velocity, "episode_return": self.fin_return,
-                "episode_length": self.fin_length}
+                "episode_length": self.fin_length, "observe_t": self.config.dt}      # observe_t: train.py:553-557 (constant dt)
+        if self.term_local_map is not None:
+            info["terminal_local_map"] = self.term_local_map
+        return info
 
     @staticmethod
     def decode_flags(flags):

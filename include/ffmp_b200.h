@@ -169,6 +169,12 @@ int ffmp_learner_input(ffmp_handle *h, void *out_dev, int32_t dtype, float scale
 int ffmp_scan(ffmp_handle *h, int32_t beams, float range_max, float *scan_dev, uint8_t *hit_dev, void *stream);
 
 /* Make `stream` wait (device-side, no host sync) for all queued background regeneration. */
+/* Terminal observations (SPEC.md §7; the reference's last tick of an episode, /root/reference/src/train.py:611-664):
+ * term_frames_dev = caller-allocated u8[N][2][W][W] or NULL (off, the default).  When set, every ffmp_step / ffmp_rollout /
+ * ffmp_step_host tick is followed by one small kernel that writes, for the envs whose `done` is set, the terminal local_map
+ * [previous frame, crop at the terminal pose on the finished episode's flow image]; rows of other envs are left untouched. */
+int ffmp_set_terminal_obs(ffmp_handle *h, uint8_t *term_frames_dev);
+
 int ffmp_join(ffmp_handle *h, void *stream);
 
 /* Device error word accumulated by the kernels (bit0: action id out of range). Synchronises `stream`. */

@@ -73,6 +73,7 @@ _ENV_FIELDS = {
     "cost": (C.c_int32, np.int32), "pose": (C.c_float, np.float32), "goal": (C.c_float, np.float32),
     "d_first": (C.c_float, np.float32), "ep_return": (C.c_float, np.float32), "steps": (C.c_int32, np.int32),
     "goal_cell": (C.c_int32, np.int32), "episode": (C.c_uint32, np.uint32), "local_map": (C.c_uint8, np.uint8),
+    "term_local_map": (C.c_uint8, np.uint8),
     "rel_goal": (C.c_float, np.float32), "velocity": (C.c_float, np.float32), "reward": (C.c_float, np.float32),
     "done": (C.c_uint8, np.uint8), "flags": (C.c_uint8, np.uint8), "term_rel_goal": (C.c_float, np.float32),
     "term_velocity": (C.c_float, np.float32), "fin_return": (C.c_float, np.float32), "fin_length": (C.c_int32, np.int32),
@@ -145,7 +146,7 @@ class OracleVectorEnv:
         N, G, W = num_envs, grid, window
         shapes = {"occ": (N, G, G), "dir": (N, G, G), "flow": (N, G, G), "cost": (N, G, G), "pose": (N, 3),
                   "goal": (N, 2), "d_first": (N,), "ep_return": (N,), "steps": (N,), "goal_cell": (N, 2),
-                  "episode": (N,), "local_map": (N, 2, W, W), "rel_goal": (N, 2), "velocity": (N, 2),
+                  "episode": (N,), "local_map": (N, 2, W, W), "term_local_map": (N, 2, W, W), "rel_goal": (N, 2), "velocity": (N, 2),
                   "reward": (N,), "done": (N,), "flags": (N,), "term_rel_goal": (N, 2), "term_velocity": (N, 2),
                   "fin_return": (N,), "fin_length": (N,)}
         for name, shp in shapes.items():

@@ -372,6 +372,7 @@ typedef struct {
     uint32_t *episode;           /* [N] */
     /* outputs */
     uint8_t *local_map;          /* [N,2,W,W] */
+    uint8_t *term_local_map;     /* [N,2,W,W] terminal observation of the envs that finished in the last step (SPEC.md §7) */
     float *rel_goal, *velocity;  /* [N,2] */
     float *reward;               /* [N] */
     uint8_t *done, *flags;       /* [N] */
@@ -422,6 +423,7 @@ orc_env *orc_env_create(int N, int G, int W, int max_steps, int goal_mode, uint3
     e->steps = calloc(N, sizeof(int32_t)); e->goal_cell = calloc(N * 2, sizeof(int32_t));
     e->episode = calloc(N, sizeof(uint32_t));
     e->local_map = calloc(N * 2 * ww, 1);
+    e->term_local_map = calloc(N * 2 * ww, 1);
     e->rel_goal = calloc(N * 2, sizeof(float)); e->velocity = calloc(N * 2, sizeof(float));
     e->reward = calloc(N, sizeof(float)); e->done = calloc(N, 1); e->flags = calloc(N, 1);
     e->term_rel_goal = calloc(N * 2, sizeof(float)); e->term_velocity = calloc(N * 2, sizeof(float));
@@ -432,7 +434,7 @@ orc_env *orc_env_create(int N, int G, int W, int max_steps, int goal_mode, uint3
 void orc_env_destroy(orc_env *e) {
     free(e->occ); free(e->dir); free(e->flow); free(e->cost); free(e->pose); free(e->goal);
     free(e->d_first); free(e->ep_return); free(e->steps); free(e->goal_cell); free(e->episode);
-    free(e->local_map); free(e->rel_goal); free(e->velocity); free(e->reward); free(e->done); free(e->flags);
+    free(e->local_map); free(e->term_local_map); free(e->rel_goal); free(e->velocity); free(e->reward); free(e->done); free(e->flags);
     free(e->term_rel_goal); free(e->term_velocity); free(e->fin_return); free(e->fin_length);
     free(e);
 }
@@ -482,6 +484,11 @@ void orc_env_step(orc_env *e, const int64_t *actions) {
         e->term_rel_goal[2 * n] = d; e->term_rel_goal[2 * n + 1] = bearing;
         e->term_velocity[2 * n] = vl; e->term_velocity[2 * n + 1] = va;
         if (done) {
+            /* terminal observation (a15, train.py:611-664: the last tick's obs): [previous newest frame, crop at the
+             * terminal pose on the finished episode's flow image], taken before the next scenario replaces it */
+            uint8_t *lm = e->local_map + (size_t)n * 2 * ww, *tm = e->term_local_map + (size_t)n * 2 * ww;
+            memcpy(tm, lm + ww, ww);
+            orc_crop(e->flow + n * gg, e->G, e->W, ci, cj, tm + ww);
             e->fin_return[n] = e->ep_return[n];
             e->fin_length[n] = e->steps[n];
             e->episode[n] += 1;
@@ -502,7 +509,7 @@ void orc_env_step(orc_env *e, const int64_t *actions) {
 GETTER(uint8_t, occ) GETTER(uint8_t, dir) GETTER(uint8_t, flow) GETTER(int32_t, cost)
 GETTER(float, pose) GETTER(float, goal) GETTER(float, d_first) GETTER(float, ep_return)
 GETTER(int32_t, steps) GETTER(int32_t, goal_cell) GETTER(uint32_t, episode)
-GETTER(uint8_t, local_map) GETTER(float, rel_goal) GETTER(float, velocity) GETTER(float, reward)
+GETTER(uint8_t, local_map) GETTER(uint8_t, term_local_map) GETTER(float, rel_goal) GETTER(float, velocity) GETTER(float, reward)
 GETTER(uint8_t, done) GETTER(uint8_t, flags) GETTER(float, term_rel_goal) GETTER(float, term_velocity)
 GETTER(float, fin_return) GETTER(int32_t, fin_length)
 uint32_t orc_env_error_word(orc_env *e) { return e->error_word; }

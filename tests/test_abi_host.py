@@ -100,3 +100,19 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "ffmp_oracle" not in text, f
+
+
+def test_gym_ffmp_import_shim_mirrors_reference_module_paths():
+    """`import gym_ffmp` + the module paths train.py:35-37 uses resolve to the CUDA-backed objects (no compute here)."""
+    import importlib
+    import sys
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    gym_ffmp = importlib.import_module("gym_ffmp")
+    cfg = importlib.import_module("gym_ffmp.envs.robot.config")
+    env_mod = importlib.import_module("gym_ffmp.envs.ffmp")
+    assert env_mod.FFMP is ffmp.FFMP and importlib.import_module("gym_ffmp.envs").FFMP is ffmp.FFMP
+    assert cfg.RobotAction is ffmp.RobotAction and cfg.RobotPose is ffmp.RobotPose
+    assert cfg.RobotVelocity is ffmp.RobotVelocity and cfg.RobotState is ffmp.RobotState
+    assert gym_ffmp.ENV_ID == "FFMP-v0" and callable(gym_ffmp.make)
+    assert (env_mod.MAP_GRID_NUM, env_mod.MAP_RESOLUTION, env_mod.GOAL_THRESHOLD) == (100, 0.05, 0.5)      # ffmp.py:14-19

@@ -2,12 +2,16 @@
 seeded inputs.  Integer / byte work is bit-exact; the fp32 SPEC (fixed operation order, no FMA) makes
 poses, rewards and observations bit-exact too, which is stricter than the 1e-5 tolerance of the
 north star (asserted as well so a future relaxation stays visible)."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 import oracle
 from maps import special_cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -186,8 +190,8 @@ def compare_env(env, orc, t, check_planes=False):
         assert np.array_equal(t2n(env.flow_dir()), orc.dir), (t, "dir")
 
 
-def rollout_parity(ffmp, N, steps, seed=0, check_every=50, **kw):
-    env = ffmp.FFMPVectorEnv(N, seed=seed, **kw)
+def rollout_parity(ffmp, N, steps, seed=0, check_every=50, terminal_obs=True, **kw):
+    env = ffmp.FFMPVectorEnv(N, seed=seed, terminal_obs=terminal_obs, **kw)
     okw = {k: v for k, v in kw.items() if k in ("grid", "window", "max_steps", "goal_mode", "p_occ", "block_shift", "env_id_base", "dt")}
     orc = oracle.OracleVectorEnv(N, seed=seed, **okw)
     env.reset()
@@ -210,6 +214,9 @@ def rollout_parity(ffmp, N, steps, seed=0, check_every=50, **kw):
         if d.any():
             assert np.array_equal(t2n(info["episode_return"])[d].view(np.uint32), orc.fin_return[d].view(np.uint32)), t
             assert np.array_equal(t2n(info["episode_length"])[d], orc.fin_length[d]), t
+            if terminal_obs:      # a15: the terminal observation of the envs that finished ([previous frame, terminal crop])
+                assert np.array_equal(t2n(info["terminal_local_map"])[d], orc.term_local_map[d]), (t, "terminal_local_map")
+        assert info["observe_t"] == env.config.dt
         ndone += int(d.sum())
         compare_env(env, orc, t, check_planes=(t % check_every == check_every - 1))
     assert env.error_word() == 0
@@ -234,7 +241,10 @@ def test_rollout_config1_default_grid(ffmp):
 
 @pytest.mark.parametrize("ring,slots", [(2, 3), (3, 2), (5, 4), (8, 3)])
 def test_rollout_ring_and_slot_variants(ffmp, ring, slots):
+    # (the (3, 2) case also runs without the terminal-observation kernel: the default configuration of the env)
     rollout_parity(ffmp, 32, 150, seed=7, grid=64, window=32, ring=ring, slots=slots, max_steps=12, check_every=30)
+    if (ring, slots) == (3, 2):
+        rollout_parity(ffmp, 32, 60, seed=8, grid=64, window=32, ring=ring, slots=slots, max_steps=12, check_every=30, terminal_obs=False)
 
 
 def test_rollout_dense_obstacles_short_episodes(ffmp):
@@ -394,6 +404,29 @@ def test_compat_object_against_reference_golden(ffmp, golden):
     for case in golden["rewarder2"]:
         r, d, g = env.rewarder2(case["scan"], case["rel_goal"], case["is_first"])
         assert abs(r - case["expect"][0]) <= 1e-5 and [d, g] == case["expect"][1:], case
+
+
+def test_gym_make_through_the_gym_ffmp_shim(ffmp, golden, monkeypatch):
+    """train.py:35,456: `import gym_ffmp; gym.make('FFMP-v0')` — with a `gym` importable (here the stand-in registry of
+    oracle/gym_shim, test infrastructure) the id resolves to the CUDA-backed FFMP object; train.py:577's only env call,
+    rewarder2, answers as the reference does."""
+    import importlib
+    import sys
+    monkeypatch.syspath_prepend(os.path.join(ROOT, "oracle", "gym_shim"))
+    monkeypatch.syspath_prepend(ROOT)
+    for m in [k for k in sys.modules if k == "gym" or k.startswith("gym.") or k == "gym_ffmp" or k.startswith("gym_ffmp.")]:
+        monkeypatch.delitem(sys.modules, m)
+    gym = importlib.import_module("gym")
+    gym_ffmp = importlib.import_module("gym_ffmp")
+    assert "gym" in gym_ffmp.REGISTERED_WITH
+    env = gym.make("FFMP-v0")
+    assert isinstance(env, ffmp.FFMP)
+    for case in golden["rewarder2"]:
+        r, d, g = env.rewarder2(case["scan"], case["rel_goal"], case["is_first"])
+        assert abs(r - case["expect"][0]) <= 1e-5 and [d, g] == case["expect"][1:], case
+    obs = env.reset()
+    assert obs["local_map"].shape == (100, 100, 1) and obs["local_map"].dtype == np.int32
+    env.close()
 
 
 def test_env_collision_equals_reference_is_collision_on_crop(ffmp, cuda_device):
