@@ -5,6 +5,7 @@ from .robot import NUM_ACTIONS, RobotAction, RobotPose, RobotState, RobotVelocit
 from .vector_env import FFMPConfig, FFMPVectorEnv, make_spaces, p_threshold  # noqa: F401
 from . import native, ops, spaces  # noqa: F401
 from .replay import ReplayRing  # noqa: F401
+from .qnet import QNetwork  # noqa: F401
 
 __all__ = ["FFMP", "FFMPConfig", "FFMPVectorEnv", "RobotAction", "RobotPose", "RobotState", "RobotVelocity",
-           "NUM_ACTIONS", "make", "register", "make_spaces", "ops", "spaces", "native", "ReplayRing"]
+           "NUM_ACTIONS", "make", "register", "make_spaces", "ops", "spaces", "native", "ReplayRing", "QNetwork"]

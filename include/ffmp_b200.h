@@ -251,6 +251,24 @@ int ffmp_op_reward_calculator(int32_t device, int32_t n, const float *rel_goal_d
                               const uint8_t *is_first_dev, float *d_first_dev, float *reward_dev, uint8_t *done_dev,
                               uint8_t *flags_dev, void *stream);
 
+/* ---- Q network of the reference trainer -------------------------------------------------------------
+ * Network.forward(state_m, state_g, state_v, state_t) of /root/reference/src/train.py:231-303 as tcgen05 implicit-GEMM kernels
+ * (csrc/qnet.cu): bf16 operands, fp32 accumulation in TMEM.  Weights are given in the layouts of the module's state_dict
+ * (f32, device), in the order conv1, conv2, conv3, conv4, fc1, fc2, fc3, fc4_ea, fc4_ev; ffmp_qnet_load converts them once.
+ * state_m: [B][2][100][100] NCHW, dtype 1 = bfloat16 (what ffmp_learner_input writes), 0 = float32; state_g / state_v f32
+ * [B][2], state_t f32 [B][1]; q_out f32 [B][28].  scalar_tile != 0 keeps the reference's scalar tile x_gvt_[0][30]
+ * (train.py:264-276: the only path by which goal / velocity / dt reach the output); 0 leaves it out. */
+typedef struct ffmp_qnet ffmp_qnet;
+int ffmp_qnet_create(int32_t device, int32_t max_batch, ffmp_qnet **out);
+int ffmp_qnet_load(ffmp_qnet *n, const float *const *weights_dev, const float *const *biases_dev, void *stream);
+int ffmp_qnet_forward(ffmp_qnet *n, int32_t batch, const void *state_m_dev, int32_t dtype, const float *state_g_dev,
+                      const float *state_v_dev, const float *state_t_dev, int32_t scalar_tile, float *q_out_dev, void *stream);
+/* layer 1..6: the six convolution outputs (bf16 NHWC), 7: fc2, 8: fc3 (bf16 [B][512]); out_dev may be NULL (size query) */
+int ffmp_qnet_debug_activation(ffmp_qnet *n, int32_t layer, int32_t batch, void *out_dev, size_t *elems_per_sample, void *stream);
+int ffmp_qnet_launch_count(const ffmp_qnet *n, uint64_t *out);
+int ffmp_qnet_destroy(ffmp_qnet *n);
+const char *ffmp_qnet_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif
