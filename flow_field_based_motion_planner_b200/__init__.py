@@ -6,6 +6,7 @@ from .vector_env import FFMPConfig, FFMPVectorEnv, make_spaces, p_threshold  # n
 from . import native, ops, spaces  # noqa: F401
 from .replay import ReplayRing  # noqa: F401
 from .qnet import QNetwork  # noqa: F401
+from .learner import DDQNLearner, TorchNetwork  # noqa: F401
 
 __all__ = ["FFMP", "FFMPConfig", "FFMPVectorEnv", "RobotAction", "RobotPose", "RobotState", "RobotVelocity",
-           "NUM_ACTIONS", "make", "register", "make_spaces", "ops", "spaces", "native", "ReplayRing", "QNetwork"]
+           "NUM_ACTIONS", "make", "register", "make_spaces", "ops", "spaces", "native", "ReplayRing", "QNetwork", "DDQNLearner", "TorchNetwork"]

@@ -16,6 +16,7 @@ EXPORTS = [
     "ffmp_reset", "ffmp_step", "ffmp_rollout", "ffmp_step_host", "ffmp_step_host_async", "ffmp_step_host_wait", "ffmp_obs_slot", "ffmp_set_obs_slot", "ffmp_set_terminal_obs", "ffmp_join", "ffmp_error_word", "ffmp_timing", "ffmp_launch_count", "ffmp_debug_trace", "ffmp_learner_input", "ffmp_scan", "ffmp_op_scan",
     "ffmp_feed_create", "ffmp_feed_handle", "ffmp_feed_connect", "ffmp_feed_info", "ffmp_feed_push", "ffmp_feed_wait", "ffmp_feed_release", "ffmp_feed_error", "ffmp_feed_destroy", "ffmp_pack_transitions",
     "ffmp_op_scenarios", "ffmp_op_flow_field_workspace", "ffmp_op_flow_field", "ffmp_op_rewarder", "ffmp_op_rewarder2", "ffmp_op_reward_calculator",
+    "ffmp_replay_gather",
     "ffmp_qnet_create", "ffmp_qnet_load", "ffmp_qnet_forward", "ffmp_qnet_debug_activation", "ffmp_qnet_launch_count", "ffmp_qnet_destroy", "ffmp_qnet_last_error",
 ]
 
@@ -75,6 +76,7 @@ def lib() -> C.CDLL:
     L.ffmp_obs_slot.argtypes = [vp, C.POINTER(i32)]
     L.ffmp_set_obs_slot.argtypes = [vp, i32]
     L.ffmp_join.argtypes = [vp, vp]
+    L.ffmp_replay_gather.argtypes = [i32, vp, C.c_size_t, i32, i32, i32, vp, vp, i32] + [vp] * 10
     L.ffmp_qnet_last_error.restype = C.c_char_p
     L.ffmp_qnet_create.argtypes = [i32, i32, C.POINTER(vp)]
     L.ffmp_qnet_load.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), vp]

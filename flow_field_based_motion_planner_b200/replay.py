@@ -74,3 +74,33 @@ class ReplayRing:
                 "action": self.actions[t1, e], "observe_m": self.maps[t1, e], "observe_g": self.rel_goal[t1, e],
                 "observe_v": self.velocity[t1, e], "reward": self.reward[t1, e], "done": self.done[t1, e],
                 "index": torch.stack([k, e], 1)}
+
+    def sample_learner(self, batch_size: int, generator=None, out=None):
+        """The same uniform minibatch in the learner's formats, gathered by ONE kernel (csrc/replay.cu): observation stacks as
+        bf16 NCHW [B,2,W,W] (the Q network's input; the u8 -> bf16 widening is fused into the gather), state_g / state_v /
+        observe_g / observe_v f32 [B,2], reward f32 [B], done u8 [B], action i64 [B].  `out` reuses a previous result's tensors."""
+        stored = min(self.count, self.T)
+        if stored < 2:
+            raise ValueError("the ring holds no complete transition yet")
+        dev = self.env.device
+        newest = self.count - 1
+        k = newest - torch.randint(0, stored - 1, (batch_size,), device=dev, generator=generator)
+        e = torch.randint(0, self.N, (batch_size,), device=dev, generator=generator)
+        index = torch.stack([k, e], 1).contiguous()
+        B, W = batch_size, self.W
+        if out is None:
+            out = {"state_m": torch.empty((B, 2, W, W), dtype=torch.bfloat16, device=dev),
+                   "observe_m": torch.empty((B, 2, W, W), dtype=torch.bfloat16, device=dev),
+                   "state_g": torch.empty((B, 2), device=dev), "state_v": torch.empty((B, 2), device=dev),
+                   "observe_g": torch.empty((B, 2), device=dev), "observe_v": torch.empty((B, 2), device=dev),
+                   "reward": torch.empty((B,), device=dev), "done": torch.empty((B,), dtype=torch.uint8, device=dev),
+                   "action": torch.empty((B,), dtype=torch.int64, device=dev)}
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        p = lambda t: C.c_void_p(t.data_ptr())      # noqa: E731
+        rc = self._L.ffmp_replay_gather(dev.index, p(self.blocks), self.stride, self.T, self.N, W, p(self.actions), p(index), B,
+                                        p(out["state_m"]), p(out["observe_m"]), p(out["state_g"]), p(out["state_v"]),
+                                        p(out["observe_g"]), p(out["observe_v"]), p(out["reward"]), p(out["done"]),
+                                        p(out["action"]), stream)
+        native.check(rc, "ffmp_replay_gather")
+        out["index"] = index
+        return out

@@ -251,6 +251,14 @@ int ffmp_op_reward_calculator(int32_t device, int32_t n, const float *rel_goal_d
                               const uint8_t *is_first_dev, float *d_first_dev, float *reward_dev, uint8_t *done_dev,
                               uint8_t *flags_dev, void *stream);
 
+/* Minibatch gather of a replay ring of packed transition blocks (ReplayMemory.sample + Brain.make_minibatch,
+ * /root/reference/src/train.py:224-225, 349-369) in one kernel: index i64 [B][2] = (push number k >= 1, env e); state = push
+ * k-1, action / reward / done / next observation = push k.  Observation stacks come out as bf16 NCHW [B][2][W][W]. */
+int ffmp_replay_gather(int32_t device, const uint8_t *blocks_dev, size_t stride, int32_t T, int32_t N, int32_t W,
+                       const int64_t *actions_dev, const int64_t *index_dev, int32_t B, void *state_m_bf16,
+                       void *observe_m_bf16, float *state_g, float *state_v, float *observe_g, float *observe_v,
+                       float *reward, uint8_t *done, int64_t *action, void *stream);
+
 /* ---- Q network of the reference trainer -------------------------------------------------------------
  * Network.forward(state_m, state_g, state_v, state_t) of /root/reference/src/train.py:231-303 as tcgen05 implicit-GEMM kernels
  * (csrc/qnet.cu): bf16 operands, fp32 accumulation in TMEM.  Weights are given in the layouts of the module's state_dict

@@ -108,3 +108,66 @@ def test_qnet_consumes_learner_input(cuda_device):
     env.step(actions)
     qn.close()
     env.close()
+
+
+@pytest.mark.gpu
+def test_replay_gather_kernel_matches_strided_sample(cuda_device):
+    """ReplayRing.sample_learner (one gather kernel, bf16 NCHW) against the strided-view sample on the same indices."""
+    import flow_field_based_motion_planner_b200 as ffmp
+    env = ffmp.FFMPVectorEnv(24, grid=64, window=32, seed=3, max_steps=9, device=str(cuda_device))
+    env.reset()
+    ring = ffmp.ReplayRing(env, 6)
+    ring.push()
+    g = torch.Generator(device=cuda_device)
+    g.manual_seed(0)
+    for _ in range(9):                        # wraps the ring
+        a = torch.randint(0, 28, (24,), device=cuda_device, generator=g)
+        env.step(a)
+        ring.push(a)
+    g1 = torch.Generator(device=cuda_device); g1.manual_seed(5)
+    g2 = torch.Generator(device=cuda_device); g2.manual_seed(5)
+    ref = ring.sample(64, generator=g1)
+    got = ring.sample_learner(64, generator=g2)
+    assert torch.equal(ref["index"], got["index"])
+    assert got["state_m"].dtype == torch.bfloat16
+    assert torch.equal(got["state_m"].float(), ref["state_m"].float()) and torch.equal(got["observe_m"].float(), ref["observe_m"].float())
+    for k in ("state_g", "state_v", "observe_g", "observe_v", "reward", "done", "action"):
+        assert torch.equal(got[k], ref[k]), k
+    env.close()
+
+
+@pytest.mark.gpu
+def test_ddqn_learner_update_and_act(cuda_device):
+    """Brain.replay (train.py:316-333) on the kernels + autograd: the loss is finite, the weights move, the kernels keep
+    agreeing with the torch module after the weights were handed back, and the target net lags until update_target()."""
+    import flow_field_based_motion_planner_b200 as ffmp
+    env = ffmp.FFMPVectorEnv(8, grid=128, window=100, seed=11, max_steps=6, device=str(cuda_device))
+    obs = env.reset()
+    ring = ffmp.ReplayRing(env, 8)
+    ring.push()
+    learner = ffmp.DDQNLearner(device=str(cuda_device), max_batch=16, seed=1, dt=env.config.dt)
+    g = torch.Generator(device=cuda_device)
+    g.manual_seed(2)
+    for _ in range(5):
+        a = learner.act(env, obs, episode=0, generator=g)
+        assert a.shape == (8,) and int(a.min()) >= 0 and int(a.max()) < 28
+        obs, *_ = env.step(a)
+        ring.push(a)
+    w0 = learner.module.fc3.weight.detach().clone()
+    fc1_0 = learner.module.fc1.weight.detach().clone()
+    batch = ring.sample_learner(16, generator=g)
+    t = torch.full((16, 1), env.config.dt, device=cuda_device)
+    q_target_before = learner.target(batch["observe_m"], batch["observe_g"], batch["observe_v"], t).clone()
+    loss = learner.update(batch)
+    assert torch.isfinite(loss) and learner.updates == 1
+    assert not torch.equal(learner.module.fc3.weight, w0)
+    assert torch.equal(learner.module.fc1.weight, fc1_0)            # `.item()` (train.py:265): fc1 never trains
+    with torch.no_grad():
+        q_mod = learner.module.eval()(batch["state_m"].float(), batch["state_g"], batch["state_v"], t)
+    q_ker = learner.main(batch["state_m"], batch["state_g"], batch["state_v"], t)
+    assert float((q_ker - q_mod).abs().max()) <= 0.03 * float(q_mod.max() - q_mod.min()) + 1e-3
+    assert torch.equal(learner.target(batch["observe_m"], batch["observe_g"], batch["observe_v"], t), q_target_before)
+    learner.update_target()
+    assert not torch.equal(learner.target(batch["observe_m"], batch["observe_g"], batch["observe_v"], t), q_target_before)
+    learner.close()
+    env.close()
