@@ -594,10 +594,15 @@ static bool rows_for_small() {
 }
 cudaError_t launch_flow_field_large(const FlowArgs &a, int grid, cudaStream_t st);
 cudaError_t launch_flow_field_il(const FlowArgs &a, int grid, cudaStream_t st);      // flow_field_il.cu: 96 < G <= 128
+cudaError_t launch_flow_field_wide(const FlowArgs &a, int grid, cudaStream_t st);    // flow_field_wide.cu: 384 < G <= 512
+bool flow_field_wide_supported(int G);
+size_t flow_field_wide_scratch_words();
+int flow_field_wide_max_grid();
 
 bool flow_field_supported(int G) { return (G >= 16 && G <= 128 && (G % 4) == 0) || flow_field_large_supported(G); }
 
 size_t flow_field_scratch_words(int G) {
+    if (flow_field_wide_supported(G)) return flow_field_wide_scratch_words();
     if (G > 128) return flow_field_large_scratch_words(G);
     if (flow_field_rows_usable(G)) return flow_field_large_scratch_words(G);     // >= the warp kernel's need
     // planes NPS..15 of the padded grid ((G+31)/32*32)^2 live in the per-CTA scratch (L2 resident)
@@ -607,6 +612,7 @@ size_t flow_field_scratch_words(int G) {
 
 int flow_field_il_ctas_per_sm();
 int flow_field_max_grid(int G) {
+    if (flow_field_wide_supported(G)) return flow_field_wide_max_grid();
     if (G > 128) return flow_field_large_max_grid(G);
     const int wpr = (G + 31) / 32;
     if (wpr == 4) return 148 * flow_field_il_ctas_per_sm();
@@ -618,6 +624,7 @@ int flow_field_max_grid(int G) {
 
 cudaError_t launch_flow_field(const FlowArgs &a_in, int grid, cudaStream_t st) {
     if (grid <= 0) return cudaSuccess;
+    if (flow_field_wide_supported(a_in.G)) return launch_flow_field_wide(a_in, grid, st);
     if (a_in.G > 128 || (flow_field_rows_usable(a_in.G) && rows_for_small())) return launch_flow_field_large(a_in, grid, st);
     FlowArgs a = a_in;
     a.neg1 = 0xFFFFFFFFu;

@@ -189,5 +189,98 @@ FFMP_HD void cost_row_words(const uint32_t (&bin)[7][4], const uint32_t (&V)[4],
     for (int b = 0; b < 32; ++b) out[b] = widen_cost4(x[b], par);
 }
 
+
+// ---- wide rows (large maps): WPR interleaved words per row, word w = the columns c % WPR == w, bit b <-> column b * WPR + w ----
+// The four columns b * WPR + 4j .. + 3 are bit b of words 4j .. 4j+3, so every group j of four words goes through the same
+// transposes as a 128-column row and yields, per b, the 4 cells at columns b * WPR + 4j.
+template <int WPR> FFMP_HD uint32_t ilw_lo(const uint32_t (&x)[WPR], int w) { return w > 0 ? x[w - 1] : x[WPR - 1] << 1; }
+template <int WPR> FFMP_HD uint32_t ilw_hi(const uint32_t (&x)[WPR], int w) { return w < WPR - 1 ? x[w + 1] : x[0] >> 1; }
+
+template <int WPR>
+struct RowInW {
+    uint32_t b1c[WPR], b2c[WPR], Vc[WPR], Fc[WPR];
+    uint32_t b1u[WPR], b2u[WPR], Vu[WPR];      // row R-1 (a free neighbour of a reached cell is reached: V stands in for F)
+    uint32_t b1d[WPR], b2d[WPR], Vd[WPR];      // row R+1
+};
+
+// direction_nibbles for a wide row; n[q][w] as above (WPR even: cost bit 0 of word w's cells is par0 ^ (w & 1))
+template <int WPR>
+FFMP_HD void direction_nibbles_w(const RowInW<WPR> &in, uint32_t par0, uint32_t (&n)[4][WPR]) {
+#pragma unroll
+    for (int w = 0; w < WPR; ++w) {
+        const uint32_t b0 = ((par0 ^ static_cast<uint32_t>(w)) & 1u) ? 0xFFFFFFFFu : 0u;
+        const uint32_t own = in.Vc[w];
+        const uint32_t t = in.b1c[w] ^ ~b0;
+        const uint32_t u = in.b2c[w] ^ ~in.b1c[w];
+        const uint32_t lE = own & in.Vd[w] & ~(in.b1d[w] ^ t);
+        const uint32_t lW = own & in.Vu[w] & ~(in.b1u[w] ^ t);
+        const uint32_t lN = own & ilw_hi<WPR>(in.Vc, w) & ~(ilw_hi<WPR>(in.b1c, w) ^ t);
+        const uint32_t lS = own & ilw_lo<WPR>(in.Vc, w) & ~(ilw_lo<WPR>(in.b1c, w) ^ t);
+        const uint32_t fE = in.Vd[w], fW = in.Vu[w], fN = ilw_hi<WPR>(in.Vc, w), fS = ilw_lo<WPR>(in.Vc, w);
+        const uint32_t lNE = own & ilw_hi<WPR>(in.Vd, w) & fE & fN & (ilw_hi<WPR>(in.b1d, w) ^ in.b1c[w]) & ~(ilw_hi<WPR>(in.b2d, w) ^ u);
+        const uint32_t lNW = own & ilw_hi<WPR>(in.Vu, w) & fW & fN & (ilw_hi<WPR>(in.b1u, w) ^ in.b1c[w]) & ~(ilw_hi<WPR>(in.b2u, w) ^ u);
+        const uint32_t lSW = own & ilw_lo<WPR>(in.Vu, w) & fW & fS & (ilw_lo<WPR>(in.b1u, w) ^ in.b1c[w]) & ~(ilw_lo<WPR>(in.b2u, w) ^ u);
+        const uint32_t lSE = own & ilw_lo<WPR>(in.Vd, w) & fE & fS & (ilw_lo<WPR>(in.b1d, w) ^ in.b1c[w]) & ~(ilw_lo<WPR>(in.b2d, w) ^ u);
+        const uint32_t anyD = lNE | lNW | lSW | lSE;
+        const uint32_t m0 = (anyD & lNE) | (~anyD & lE);
+        const uint32_t m1 = (anyD & lNW) | (~anyD & lN);
+        const uint32_t m2 = (anyD & lSW) | (~anyD & lW);
+        const uint32_t m3 = (anyD & lSE) | (~anyD & lS);
+        const uint32_t d1 = ~m0 & (m1 | (~m2 & m3));
+        const uint32_t d2 = ~m0 & ~m1 & (m2 | m3);
+        const uint32_t some = m0 | m1 | m2 | m3;
+        const uint32_t zero = some & ~(anyD | d1 | d2);
+        n[0][w] = anyD | zero;
+        n[1][w] = d1;
+        n[2][w] = d2;
+        n[3][w] = ~in.Fc[w] | zero;
+    }
+}
+
+// the flow words of word group j of a wide row: out[b] = the 4 flow bytes at columns b * WPR + 4j .. + 3
+template <int WPR>
+FFMP_HD void flow_group_words(const uint32_t (&n)[4][WPR], int j, uint32_t (&out)[32]) {
+    uint32_t x[16];
+#pragma unroll
+    for (int wl = 0; wl < 4; ++wl)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) x[4 * wl + q] = n[q][4 * j + wl];
+    transpose16x2(x);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        out[m] = flow_lookup(x[m]);
+        out[16 + m] = flow_lookup(x[m] >> 16);
+    }
+}
+
+// T_lo / T_hi = transposed plane words of 4 cells: T_lo byte w = (cost & 0xFE) | not-reached (0xFF where not reached), T_hi byte w =
+// cost bits 8..15 (anything where not reached).  -> the four int32 costs, 0x7FFFFFFF where not reached.
+FFMP_HD Int4 widen_cost4_16(uint32_t T_lo, uint32_t T_hi, uint32_t par) {
+    const uint32_t cst = T_lo | par;
+    const uint32_t m4 = prmt(T_lo << 7, 0u, 0xba98u);           // 0xFF per byte where not reached
+    const uint32_t hi = T_hi | m4;                              // second byte: cost bits 8..15, 0xFF where not reached
+    const uint32_t h4 = m4 & 0x7F7F7F7Fu;
+    const uint32_t a01 = prmt(cst, hi, 0x5140u), a23 = prmt(cst, hi, 0x7362u);      // (c0 h0 c1 h1) / (c2 h2 c3 h3)
+    const uint32_t mh = prmt(m4, h4, 0x5410u);                  // (m0 m1 x0 x1): third byte source / top byte source for cells 0, 1
+    const uint32_t mh2 = prmt(m4, h4, 0x7632u);                 // ... for cells 2, 3
+    Int4 o;
+    o.x = static_cast<int32_t>(prmt(a01, mh, 0x6410u));          // (c0, h0, m0, x0)
+    o.y = static_cast<int32_t>(prmt(a01, mh, 0x7532u));          // (c1, h1, m1, x1)
+    o.z = static_cast<int32_t>(prmt(a23, mh2, 0x6410u));
+    o.w = static_cast<int32_t>(prmt(a23, mh2, 0x7532u));
+    return o;
+}
+
+// bytes of 16 columns 16q .. 16q+15 of a 512-wide row -> 16 occupied flags (bit w = byte w != 0): with WPR = 16 byte w of
+// chunk q is bit q of interleaved word w, so the row's words are the 32 x 16 bit transpose of its 32 flag halfwords
+FFMP_HD uint32_t occupied_flags16(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3) {
+    // msb of every non-zero byte -> one bit per byte, gathered with a multiply (bits 7, 15, 23, 31 -> a nibble)
+    const uint32_t f0 = ((nonzero_msb(x0) >> 7) * 0x00204081u) >> 21 & 0xFu;
+    const uint32_t f1 = ((nonzero_msb(x1) >> 7) * 0x00204081u) >> 21 & 0xFu;
+    const uint32_t f2 = ((nonzero_msb(x2) >> 7) * 0x00204081u) >> 21 & 0xFu;
+    const uint32_t f3 = ((nonzero_msb(x3) >> 7) * 0x00204081u) >> 21 & 0xFu;
+    return f0 | (f1 << 4) | (f2 << 8) | (f3 << 12);
+}
+
 }  // namespace rowops
 }  // namespace ffmp

@@ -32,6 +32,8 @@ def host():
     L.host_occupied_nibbles.argtypes = [C.c_uint32] * 4
     L.il_emulate_grid.restype = C.c_int
     L.il_emulate_grid.argtypes = [u8p, C.c_int, C.c_int, C.c_int, i32p, u8p]
+    L.ilw_emulate_grid.restype = C.c_int
+    L.ilw_emulate_grid.argtypes = [u8p, C.c_int, C.c_int, C.c_int, i32p, u8p]
     return L
 
 
@@ -96,3 +98,25 @@ def test_interleaved_algorithm_matches_oracle_on_generated_maps(host):
     for sd in range(6):
         occ, g = noise(128, 0.3, sd, values=(1, 255, 128))
         _check(host, occ, g)
+
+
+def _check_wide(host, occ, goal):
+    G = occ.shape[0]
+    occ = np.ascontiguousarray(occ, np.uint8)
+    cost = np.zeros((G, G), np.int32)
+    flow = np.zeros((G, G), np.uint8)
+    host.ilw_emulate_grid(_p(occ, C.c_uint8), G, int(goal[0]), int(goal[1]), _p(cost, C.c_int32), _p(flow, C.c_uint8))
+    ec, _, ef = oracle.flow_field(occ, goal[0], goal[1])
+    assert np.array_equal(flow, ef)
+    assert np.array_equal(cost, ec)
+
+
+@pytest.mark.parametrize("G", [416, 512])
+def test_wide_row_algorithm_matches_oracle(host, G):
+    """16 interleaved words per row (flow_field_wide.cu): two-byte cost widening, the 16 x 32 flag transpose of the input."""
+    for name, occ, goal in special_cases(G):
+        if name in ("serpentine", "rooms1", "rooms2", "noise0.05", "noise0.45", "goal_out_of_grid_hi"):
+            continue                  # keep the CPU suite short: one of each kind stays
+        _check_wide(host, occ, goal)
+    occ, _, _, cells = oracle.scenario(3, 1, 0, G, p_occ=0.3, block_shift=0)
+    _check_wide(host, occ, (cells[2], cells[3]))
