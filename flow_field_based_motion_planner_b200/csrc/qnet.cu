@@ -18,6 +18,7 @@
 #include <cuda_bf16.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <new>
 #include <string>
 
@@ -41,6 +42,7 @@ struct QGemmArgs {
     const float *bias;           // [N]
     const float *post_add;       // device scalar added after the activation (train.py:264-276) or null
     void *out;
+    int dbg_shift, dbg_bo;       // experiment (QNET_DBG_SHIFT / QNET_DBG_BO): A rows shifted in shared memory, descriptor start unaligned
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, uint32_t bar) {
@@ -58,6 +60,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// the same with the descriptors as (lo, hi) halves: an issue loop advances `lo` with one 32-bit add per MMA
+__device__ __forceinline__ void umma_f16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+                 ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -109,7 +118,7 @@ qnet_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant_
                 const int st = s % QG_STAGES, use = s / QG_STAGES;
                 if (use > 0) mbar_wait(bar_addr(QG_STAGES + st), static_cast<uint32_t>((use - 1) & 1));
                 mbar_expect_tx(bar_addr(st), tx);
-                tma_load_4d(sa_s + st * QG_A_BYTES, &tma, 64 * ki, tile * g.a_c1_step, tile * g.a_c2_step + ko,
+                tma_load_4d(sa_s + st * QG_A_BYTES, &tma, 64 * ki, tile * g.a_c1_step - g.dbg_shift, tile * g.a_c2_step + ko,
                             static_cast<int>(blockIdx.y), bar_addr(st));
                 tma_load_2d(sb_s + st * B_BYTES, &tmb, 64 * s, n0, bar_addr(st));
                 if (++ki == g.k_inner) { ki = 0; ++ko; }
@@ -123,7 +132,9 @@ qnet_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant_
                 const int st = s % QG_STAGES, use = s / QG_STAGES;
                 mbar_wait(bar_addr(st), static_cast<uint32_t>(use & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t ad = umma_desc_sw128(sa_s + st * QG_A_BYTES), bd = umma_desc_sw128(sb_s + st * B_BYTES);
+                const uint32_t a_addr = sa_s + st * QG_A_BYTES + g.dbg_shift * 128;
+                const uint64_t ad = umma_desc_sw128(a_addr) | (g.dbg_bo ? static_cast<uint64_t>((a_addr >> 7) & 7u) << 49 : 0ull);
+                const uint64_t bd = umma_desc_sw128(sb_s + st * B_BYTES);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)       // 4 x (K = 16): +32 bytes inside the 128-byte swizzle atom
                     umma_f16(tmem_d, ad + 2 * k, bd + 2 * k, IDESC, (s | k) ? 1u : 0u);
@@ -177,6 +188,165 @@ qnet_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant_
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(static_cast<uint32_t>(BN)) : "memory");
     }
+}
+
+// ---- conv1 (2 -> 32 channels, 32 x 32 kernel, train.py:236) with the whole input image resident in shared memory ------------
+// The generic kernel re-fetches every input pixel 32 x 32 times through L2 (one 128-byte K-slice per output pixel and kernel
+// tap pair): 29 GB per 256 samples, L2-bound at 4x the tensor time.  Here one CTA owns one sample: the NHWC8 image (100 x 100
+// pixels of 16 bytes = 160 KB) is copied to shared memory ONCE, in its global layout, and every A operand is a VIEW of it.
+// With the un-swizzled K-major layout a tcgen05 operand is made of 8-row x 16-byte core matrices whose rows are 16 bytes apart:
+// exactly consecutive pixels.  M row m of a tile <-> image pixel m0 + m (row pitch 100: the 31 rightmost of every 100 rows
+// are windows that run over the image edge and are discarded), K = 16 <-> the two taps kw, kw + 1, i.e. the pixels
+// m0 + m + kh * 100 + kw (+1): descriptor start = that pixel, leading byte offset 16 (next pixel), stride byte offset 128 (next
+// 8 rows).  Overlapping "rows" are only address arithmetic to the tensor core.  The weights of one kernel row (32 taps x 8
+// channels x 32 output channels = 16 KB, pre-arranged in the core-matrix order) stream through a 2-stage ring; 16 accumulators
+// of 32 columns fill TMEM, so a pass covers 2048 image pixels and a sample takes 4 passes of 32 x 16 x 16 MMAs.
+constexpr int C1_IMG = 100 * 100 * 16;            // bytes of the NHWC8 image
+constexpr int C1_IMG_PAD = C1_IMG + 8192;         // windows of discarded rows may read past the image
+constexpr int C1_WROW = 32 * 32 * 16;             // weights of one kernel row: [kw 32][oc 32][8 ch] bf16
+constexpr int C1_TILES = (68 * 100 + 68) / 128 + 1;   // 54 tiles of 128 pixels cover the last valid output pixel
+constexpr int C1_ACC = 16;                        // accumulators (32 TMEM columns each) per pass
+constexpr int C1_SMEM = C1_IMG_PAD + 2 * C1_WROW + 128;
+
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           (static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+// planar = 1: output as [4 channel chunks][69 * 69 pixels][8 channels] (the layout conv2's resident kernel views), else NHWC
+__global__ void __launch_bounds__(QG_THREADS, 1)
+qnet_conv1_kernel(const __nv_bfloat16 *in, const __nv_bfloat16 *w, const float *bias, __nv_bfloat16 *out, int planar) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *img = smem, *wst = smem + C1_IMG_PAD;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(wst + 2 * C1_WROW);     // img, wfull[2], wempty[2], accfull, accempty
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto bar_addr = [&](int i) { return static_cast<uint32_t>(__cvta_generic_to_shared(bars + i)); };
+    const uint32_t img_s = static_cast<uint32_t>(__cvta_generic_to_shared(img)), wst_s = static_cast<uint32_t>(__cvta_generic_to_shared(wst));
+    const int n = blockIdx.x;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 6; ++i) mbar_init(bar_addr(i), 1);
+        mbar_init(bar_addr(6), 4);                // accempty: one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(tmem_slot))), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // the pad behind the image is read by discarded rows only, but must not hold NaN patterns that trap nothing — just define it
+    for (int i = threadIdx.x; i < (C1_IMG_PAD - C1_IMG) / 16; i += QG_THREADS) reinterpret_cast<uint4 *>(img + C1_IMG)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot;
+    constexpr int PASSES = (C1_TILES + C1_ACC - 1) / C1_ACC;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(bar_addr(0), C1_IMG);
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(in) + static_cast<size_t>(n) * C1_IMG;
+            for (int c = 0; c < 10; ++c) tma_bulk_g2s(img_s + c * 16000, src + c * 16000, 16000, bar_addr(0));
+            int s = 0;
+            for (int p = 0; p < PASSES; ++p)
+                for (int kh = 0; kh < 32; ++kh, ++s) {
+                    const int st = s & 1, use = s >> 1;
+                    if (use > 0) mbar_wait(bar_addr(3 + st), static_cast<uint32_t>((use - 1) & 1));
+                    mbar_expect_tx(bar_addr(1 + st), C1_WROW);
+                    tma_bulk_g2s(wst_s + st * C1_WROW, reinterpret_cast<const uint8_t *>(w) + static_cast<size_t>(kh) * C1_WROW, C1_WROW, bar_addr(1 + st));
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(32 >> 3) << 17) | (8u << 24);
+            mbar_wait(bar_addr(0), 0u);
+            int s = 0;
+            for (int p = 0; p < PASSES; ++p) {
+                if (p > 0) mbar_wait(bar_addr(6), static_cast<uint32_t>((p - 1) & 1));     // the epilogue drained the accumulators
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int nt = min(C1_ACC, C1_TILES - p * C1_ACC);
+                for (int kh = 0; kh < 32; ++kh, ++s) {
+                    const int st = s & 1, use = s >> 1;
+                    mbar_wait(bar_addr(1 + st), static_cast<uint32_t>(use & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    // descriptor halves: hi = (stride byte offset, version), lo = (start >> 4, leading byte offset); only the start moves
+                    const uint64_t bd0 = umma_desc_nosw(wst_s + st * C1_WROW, 512, 128);
+                    const uint64_t ad0 = umma_desc_nosw(img_s + static_cast<uint32_t>((p * C1_ACC * 128 + kh * 100) * 16), 16, 128);
+                    const uint32_t b_hi = static_cast<uint32_t>(bd0 >> 32), a_hi = static_cast<uint32_t>(ad0 >> 32);
+                    uint32_t b_lo = static_cast<uint32_t>(bd0), a_lo0 = static_cast<uint32_t>(ad0);
+#pragma unroll 1
+                    for (int kp = 0; kp < 16; ++kp) {
+                        uint32_t a_lo = a_lo0;
+                        const uint32_t acc = (kh | kp) ? 1u : 0u;
+#pragma unroll 4
+                        for (int t = 0; t < nt; ++t) {
+                            umma_f16_lh(tmem_d + 32 * t, a_lo, a_hi, b_lo, b_hi, IDESC, acc);
+                            a_lo += 2048 >> 4;                 // next tile: 128 pixels
+                        }
+                        a_lo0 += 32 >> 4;                      // next tap pair: 2 pixels
+                        b_lo += 1024 >> 4;                     // next two 512-byte tap chunks
+                    }
+                    umma_commit(bar_addr(3 + st));
+                }
+                umma_commit(bar_addr(5));
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        for (int p = 0; p < PASSES; ++p) {
+            mbar_wait(bar_addr(5), static_cast<uint32_t>(p & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int nt = min(C1_ACC, C1_TILES - p * C1_ACC);
+            for (int t = 0; t < nt; ++t) {
+                const int m = (p * C1_ACC + t) * 128 + 32 * q + lane;
+                const int oh = m / 100, ow = m - oh * 100;
+                const bool valid = oh < 69 && ow < 69;
+                uint32_t pk[16];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem_d + (static_cast<uint32_t>(32 * q) << 16) + 32 * t + 16 * c, v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float x0 = fmaxf(__uint_as_float(v[2 * j]) + bias[16 * c + 2 * j], 0.0f);
+                        const float x1 = fmaxf(__uint_as_float(v[2 * j + 1]) + bias[16 * c + 2 * j + 1], 0.0f);
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                        pk[8 * c + j] = *reinterpret_cast<const uint32_t *>(&h);
+                    }
+                }
+                if (valid) {
+                    const size_t px = static_cast<size_t>(oh) * 69 + ow;
+                    if (planar) {
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4)
+                            *reinterpret_cast<uint4 *>(out + ((static_cast<size_t>(n) * 4 + c4) * 4761 + px) * 8) =
+                                make_uint4(pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+                    } else {
+                        uint4 *dst = reinterpret_cast<uint4 *>(out + (static_cast<size_t>(n) * 4761 + px) * 32);
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) dst[c4] = make_uint4(pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr(6)) : "memory");
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
+    }
+}
+
+// conv1 weight [32][2][32][32] f32 -> [kh][kw][oc][8] bf16 (channels 2..7 zero): the core-matrix order of the resident kernel
+__global__ void qnet_conv1_weight_core_kernel(const float *w, __nv_bfloat16 *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 32 * 32 * 32 * 8) return;
+    const int c = i & 7, oc = (i >> 3) & 31, kw = (i >> 8) & 31, kh = i >> 13;
+    out[i] = __float2bfloat16(c < 2 ? w[((oc * 2 + c) * 32 + kh) * 32 + kw] : 0.0f);
 }
 
 // ---- small helpers around the GEMMs -----------------------------------------------------------------------------------
@@ -299,6 +469,7 @@ struct ffmp_qnet {
     bool loaded = false;
     __nv_bfloat16 *w[6] = {nullptr};       // conv1, conv2, conv3, conv4, fc2, fc3 in GEMM layout; heads below
     __nv_bfloat16 *w_heads = nullptr;      // [32][512]: 28 advantage rows, the value row, 3 zero rows
+    __nv_bfloat16 *w1core = nullptr;       // conv1 weights in the core-matrix order of qnet_conv1_kernel: [kh][kw][oc][8]
     float *bias[7] = {nullptr};            // conv1..4, fc2, fc3, heads (32)
     float *fc1_w = nullptr, *fc1_b = nullptr, *scalar = nullptr, *heads_out = nullptr;
     __nv_bfloat16 *act[8] = {nullptr};     // NHWC8 input, conv1 .. conv4c outputs, fc2, fc3 outputs
@@ -317,6 +488,7 @@ int ffmp_qnet_destroy(ffmp_qnet *n) {
     cudaSetDevice(n->device);
     for (auto p : n->w) cudaFree(p);
     cudaFree(n->w_heads);
+    cudaFree(n->w1core);
     for (auto p : n->bias) cudaFree(p);
     cudaFree(n->fc1_w); cudaFree(n->fc1_b); cudaFree(n->scalar); cudaFree(n->heads_out);
     for (auto p : n->act) cudaFree(p);
@@ -351,6 +523,7 @@ int ffmp_qnet_create(int32_t device, int32_t max_batch, ffmp_qnet **out) {
     cudaError_t ce = cudaSuccess;
     for (int l = 0; l < 6 && ce == cudaSuccess; ++l) ce = cudaMalloc(&n->w[l], wsz[l] * 2);
     if (ce == cudaSuccess) ce = cudaMalloc(&n->w_heads, 32 * 512 * 2);
+    if (ce == cudaSuccess) ce = cudaMalloc(&n->w1core, 32 * 32 * 32 * 8 * 2);
     for (int l = 0; l < 7 && ce == cudaSuccess; ++l) ce = cudaMalloc(&n->bias[l], bsz[l] * 4);
     if (ce == cudaSuccess) ce = cudaMalloc(&n->fc1_w, 67 * 5 * 4);
     if (ce == cudaSuccess) ce = cudaMalloc(&n->fc1_b, 67 * 4);
@@ -363,6 +536,7 @@ int ffmp_qnet_create(int32_t device, int32_t max_batch, ffmp_qnet **out) {
         const int smem64 = QG_STAGES * (QG_A_BYTES + 64 * 128) + 256, smem32 = QG_STAGES * (QG_A_BYTES + 32 * 128) + 256;
         ce = cudaFuncSetAttribute(qnet_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(qnet_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(qnet_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM);
     }
     cudaSetDevice(prev);
     if (ce != cudaSuccess) {
@@ -386,6 +560,7 @@ int ffmp_qnet_load(ffmp_qnet *n, const float *const *weights, const float *const
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // order: conv1, conv2, conv3, conv4, fc1, fc2, fc3, fc4_ea, fc4_ev
     qnet_conv_weight_kernel<<<256, 256, 0, st>>>(weights[0], n->w[0], 32, 2, 32, 32, 8);
+    qnet_conv1_weight_core_kernel<<<1024, 256, 0, st>>>(weights[0], n->w1core);
     qnet_conv_weight_kernel<<<1024, 256, 0, st>>>(weights[1], n->w[1], 64, 32, 32, 32, 32);
     qnet_conv_weight_kernel<<<256, 256, 0, st>>>(weights[2], n->w[2], 64, 64, 8, 8, 64);
     qnet_conv_weight_kernel<<<256, 256, 0, st>>>(weights[3], n->w[3], 64, 64, 8, 8, 64);
@@ -434,7 +609,13 @@ int ffmp_qnet_forward(ffmp_qnet *n, int32_t batch, const void *state_m, int32_t 
         n->launches += 2;
     }
     // ---- the six convolutions as implicit GEMMs ----
-    for (int l = 0; l < 6; ++l) {
+    const bool conv1_resident = !std::getenv("QNET_CONV1_V1");      // development switch: the generic kernel for conv1 (A/B timing)
+    if (conv1_resident) {
+        qnet_conv1_kernel<<<B, QG_THREADS, C1_SMEM, st>>>(n->act[0], n->w1core, n->bias[0], n->act[1], 0);
+        QCK(cudaGetLastError());
+        n->launches += 1;
+    }
+    for (int l = conv1_resident ? 1 : 0; l < 6; ++l) {
         const ConvGeo &c = CONVS[l];
         CUtensorMap ta, tb;
         const cuuint64_t pix = static_cast<cuuint64_t>(c.ICP) * 2;                       // bytes per input pixel
@@ -486,6 +667,8 @@ int ffmp_qnet_forward(ffmp_qnet *n, int32_t batch, const void *state_m, int32_t 
         g.box1 = 128; g.box2 = 1; g.lim1 = B; g.lim2 = 1;
         g.ldc = f.N; g.relu = f.relu; g.out_f32 = f.f32;
         g.bias = f.bias; g.out = f.out;
+        if (const char *e = std::getenv("QNET_DBG_SHIFT")) g.dbg_shift = std::atoi(e);
+        if (const char *e = std::getenv("QNET_DBG_BO")) g.dbg_bo = std::atoi(e);
         const dim3 grid(static_cast<unsigned>((B + 127) / 128), 1, static_cast<unsigned>(f.N < 64 ? 1 : f.N / 64));
         if (f.N < 64) qnet_gemm_kernel<32><<<grid, QG_THREADS, QG_STAGES * (QG_A_BYTES + 32 * 128) + 256, st>>>(ta, tb, g);
         else qnet_gemm_kernel<64><<<grid, QG_THREADS, QG_STAGES * (QG_A_BYTES + 64 * 128) + 256, st>>>(ta, tb, g);
