@@ -325,7 +325,9 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
     }
     const int maxg = ffmp::flow_field_max_grid(cfg->grid);
     h->ff_grid = cfg->num_envs < maxg ? cfg->num_envs : maxg;
-    h->rg_grid = cfg->num_envs < REGEN_GRID ? cfg->num_envs : REGEN_GRID;
+    int rg = REGEN_GRID;
+    if (const char *e = std::getenv("FFMP_REGEN_GRID")) { const int v = std::atoi(e); if (v >= 1 && v <= REGEN_GRID) rg = v; }   // development switch
+    h->rg_grid = cfg->num_envs < rg ? cfg->num_envs : rg;
     *out = h;
     return FFMP_OK;
 }
