@@ -42,7 +42,7 @@ struct DeviceGuard {
 };
 
 constexpr int MAX_LISTS = 15;
-constexpr int REGEN_GRID = 148 * 2;   // CTAs of a background regeneration launch (grids are handed out dynamically)
+constexpr int REGEN_GRID = 148 * 2;   // CTAs of a background regeneration launch per tick of its group (grids are handed out dynamically)
 
 double now_us() {
     timespec ts;
@@ -85,12 +85,34 @@ int check_cfg(const ffmp_cfg *c) {
     if (c->goal_mode != 0 && c->goal_mode != 1) return fail(FFMP_ERR_ARG, "goal_mode must be 0 or 1");
     if (c->block_shift < 0 || c->block_shift > 8) return fail(FFMP_ERR_ARG, "block_shift must be in [0,8]");
     if (!(c->dt > 0.0f)) return fail(FFMP_ERR_ARG, "dt must be > 0");
+    if (c->regen_batch > 8 || static_cast<int>(c->regen_batch) > c->slots - 1)
+        return fail(FFMP_ERR_ARG, "regen_batch must be 0 (library default) or in [1, min(8, slots - 1)]");
     return FFMP_OK;
+}
+
+// Ticks per regeneration launch (ffmp_cfg.regen_batch).  The episode ends of m consecutive ticks share one regeneration
+// list and one background launch; between the ticks of a group nothing but the step kernel is queued, so each of them
+// starts as a programmatic dependent of the one before.  An env that ends an episode in the first tick of a group may
+// need the regenerated slot S-1 ticks later, so the floor((S-1)/m) lists are reused every nlist*m <= S-1 ticks.  The
+// default keeps at least five lists (regenerations in flight).
+int regen_batch_of(const ffmp_cfg *c) {
+    if (c->regen_batch) return static_cast<int>(c->regen_batch);
+    const int m = (c->slots - 1) / 5;
+    return m < 1 ? 1 : (m > 4 ? 4 : m);
+}
+
+// CTAs of a background regeneration launch: about one grid per CTA for the ~100 episode ends per tick of the bench
+// workload (a second round would double the launch's latency), bounded by what the kernel can keep resident.
+int regen_grid_of(const ffmp_cfg *c) {
+    const int maxg = ffmp::flow_field_max_grid(c->grid);
+    const int want = REGEN_GRID * (regen_batch_of(c) + 1) / 2;
+    const int g = want < maxg ? want : maxg;
+    return c->num_envs < g ? c->num_envs : g;
 }
 
 struct Workspace {
     size_t error_word, lists, actions, obs_order, hi, total;
-    size_t list_stride;  // bytes per regen list block: [count,ticket,pad..64B][env u32 N][episode u32 N]
+    size_t list_stride;  // bytes per regen list block: [count,ticket,pad..256B][env u32 m*N][episode u32 m*N]
 };
 
 Workspace workspace_layout(const ffmp_cfg *c) {
@@ -98,12 +120,14 @@ Workspace workspace_layout(const ffmp_cfg *c) {
     const size_t N = static_cast<size_t>(c->num_envs);
     size_t off = 0;
     w.error_word = off; off += 256;
-    w.list_stride = align_up(256 + 2 * N * sizeof(uint32_t), 256);
-    w.lists = off; off += w.list_stride * static_cast<size_t>(c->slots - 1);
+    const size_t m = static_cast<size_t>(regen_batch_of(c));
+    const size_t nlist = static_cast<size_t>(c->slots - 1) / m;
+    w.list_stride = align_up(256 + 2 * m * N * sizeof(uint32_t), 256);   // an env can end one episode per tick
+    w.lists = off; off += w.list_stride * nlist;
     w.actions = off; off += align_up(N * sizeof(int64_t), 256);
     w.obs_order = off; off += align_up(N * 8 * sizeof(uint32_t), 256);
     w.hi = off;
-    off += align_up((static_cast<size_t>(ffmp::flow_field_max_grid(c->grid)) + static_cast<size_t>(c->slots - 1) * REGEN_GRID) *
+    off += align_up((static_cast<size_t>(ffmp::flow_field_max_grid(c->grid)) + nlist * regen_grid_of(c)) *
                         ffmp::flow_field_scratch_words(c->grid) * 4, 256);
     w.total = off;
     return w;
@@ -118,6 +142,8 @@ struct ffmp_handle {
     bool bound = false, ready = false;
     cudaStream_t side[MAX_LISTS];   // one background stream per regeneration list: regenerations overlap
     int nlist = 1;
+    int batch = 1;                  // ticks per regeneration list / launch (regen_batch_of)
+    bool group_open = false;        // ticks of the current group have run and its regeneration is not launched yet
     cudaEvent_t ev_step[MAX_LISTS], ev_regen[MAX_LISTS];
     bool regen_pending[MAX_LISTS];
     uint32_t regen_seq[MAX_LISTS];  // launches of list l so far; the kernel publishes it in mapped memory (flag_host[16 + l]) when done
@@ -127,6 +153,7 @@ struct ffmp_handle {
     int rg_grid = 0;                // background regeneration grid (few items per tick)
     CUtensorMap tmap;               // flow planes as a 3-D u8 tensor for the TMA observe kernel
     bool use_tma = false;
+    bool tick_pdl = true;           // step kernels launched with the programmatic-dependent attribute (FFMP_TICK_PDL=0: off)
     bool fused = true;              // one kernel per tick (env FFMP_STEP_FUSED=0 selects dynamics + observe kernels)
     // optional per-kernel timing (ffmp_timing): events [before tick, after tick] on the caller's stream and
     // [before regeneration, after regeneration] on the side stream of the tick
@@ -134,6 +161,7 @@ struct ffmp_handle {
     bool timing = false;
     int timing_n = 0;
     cudaEvent_t tev[TIMING_RING][4];
+    bool tev_regen[TIMING_RING];    // the tick closed its group: events 2 / 3 bracket a regeneration launch
     uint64_t launches = 0;          // kernels launched by this handle (ffmp_launch_count)
     // host-buffer steps (ffmp_step_host*): completion word in mapped pinned memory, written by host_export_kernel
     volatile uint32_t *flag_host = nullptr;
@@ -160,7 +188,7 @@ struct ffmp_handle {
     uint32_t *reset_ticket() const { return error_word() + 4; }      // full-reset launches (same 256-byte header block)
     uint32_t *reset_work() const { return error_word() + 5; }
     uint32_t *list_env(int l) const { return reinterpret_cast<uint32_t *>(list_base(l) + 256); }
-    uint32_t *list_episode(int l) const { return list_env(l) + cfg.num_envs; }
+    uint32_t *list_episode(int l) const { return list_env(l) + static_cast<size_t>(batch) * cfg.num_envs; }
     int64_t *actions() const { return reinterpret_cast<int64_t *>(static_cast<char *>(b.workspace) + ws.actions); }
     uint32_t *obs_order() const { return reinterpret_cast<uint32_t *>(static_cast<char *>(b.workspace) + ws.obs_order); }
     uint32_t *hi_scratch() const { return reinterpret_cast<uint32_t *>(static_cast<char *>(b.workspace) + ws.hi); }
@@ -197,12 +225,37 @@ ffmp::StepArgs step_args(const ffmp_handle *h) {
     return a;
 }
 
+// Queue the background regeneration of the current group's list (the episode ends of its ticks so far) behind the last
+// tick on `st`, and round the tick counter up to the next group.
+int launch_regen(ffmp_handle *h, cudaStream_t st, cudaEvent_t *tev) {
+    const int l = static_cast<int>((h->step_index / static_cast<uint64_t>(h->batch)) % static_cast<uint64_t>(h->nlist));
+    CK(cudaEventRecord(h->ev_step[l], st));
+    CK(cudaStreamWaitEvent(h->side[l], h->ev_step[l], 0));
+    if (tev) CK(cudaEventRecord(tev[2], h->side[l]));
+    ffmp::FlowArgs fa = flow_args(h);
+    fa.env_idx = h->list_env(l); fa.episode = h->list_episode(l); fa.count_ptr = h->list_count(l);
+    fa.ticket = h->list_ticket(l); fa.work = h->list_work(l); fa.count_reset = h->list_count(l);
+    fa.hi_scratch = h->hi_scratch() + (static_cast<size_t>(h->ff_grid) + static_cast<size_t>(l) * h->rg_grid) * ffmp::flow_field_scratch_words(h->cfg.grid);
+    fa.host_done = h->flag_dev + 16 + l;
+    fa.host_done_value = ++h->regen_seq[l];
+    CK(ffmp::launch_flow_field(fa, h->rg_grid, h->side[l]));
+    if (tev) CK(cudaEventRecord(tev[3], h->side[l]));
+    h->launches += 1;
+    CK(cudaEventRecord(h->ev_regen[l], h->side[l]));
+    h->regen_pending[l] = true;
+    h->group_open = false;
+    h->step_index = (h->step_index / static_cast<uint64_t>(h->batch) + 1) * static_cast<uint64_t>(h->batch);
+    return FFMP_OK;
+}
+
 // One env-step-like call (mode 0 step, mode 1 masked reset) with the background regeneration queued.
 int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *mask, cudaStream_t st,
              const ffmp::HostExportArgs *host_export = nullptr) {
-    const int l = static_cast<int>(h->step_index % static_cast<uint64_t>(h->nlist));
-    if (h->regen_pending[l]) {
-        // the regeneration that last used list `l` (S-1 ticks ago) must be complete: it re-armed the
+    const uint64_t m = static_cast<uint64_t>(h->batch);
+    const int l = static_cast<int>((h->step_index / m) % static_cast<uint64_t>(h->nlist));
+    const bool first = h->step_index % m == 0, last = h->step_index % m == m - 1;
+    if (first && h->regen_pending[l]) {
+        // the regeneration that last used list `l` (nlist groups ago) must be complete: it re-armed the
         // list and filled the scenario slot an env may switch to in this tick.  If the host already sees it complete
         // (the usual case when the caller synchronises every step) no device-side wait is queued in front of the tick.
         // The regeneration kernel's last CTA publishes its launch number in mapped host memory: one plain load tells whether
@@ -224,7 +277,9 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
     const bool one_kernel = h->use_tma && h->fused;
     cudaEvent_t *tev = (h->timing && h->timing_n < ffmp_handle::TIMING_RING) ? h->tev[h->timing_n++] : nullptr;
     if (tev) CK(cudaEventRecord(tev[0], st));
-    CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st, nullptr, h->fused));
+    // the step kernel is always launched as a programmatic dependent of whatever precedes it on the stream (it touches no
+    // global memory before its griddepcontrol.wait): behind another step kernel its CTAs are resident when that one drains
+    CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st, nullptr, h->fused, h->tick_pdl));
     if (h->io_stats) h->t_tick = now_us();
     if (host_export) {
         // directly behind the step kernel (nothing in between), so that the programmatic dependency pairs the two
@@ -239,22 +294,14 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
         CK(ffmp::launch_terminal_obs(a, st));
         h->launches += 1;
     }
-    CK(cudaEventRecord(h->ev_step[l], st));
-    CK(cudaStreamWaitEvent(h->side[l], h->ev_step[l], 0));
-    if (tev) CK(cudaEventRecord(tev[2], h->side[l]));
-    ffmp::FlowArgs fa = flow_args(h);
-    fa.env_idx = h->list_env(l); fa.episode = h->list_episode(l); fa.count_ptr = h->list_count(l);
-    fa.ticket = h->list_ticket(l); fa.work = h->list_work(l); fa.count_reset = h->list_count(l);
-    fa.hi_scratch = h->hi_scratch() + (static_cast<size_t>(h->ff_grid) + static_cast<size_t>(l) * h->rg_grid) * ffmp::flow_field_scratch_words(h->cfg.grid);
-    fa.host_done = h->flag_dev + 16 + l;
-    fa.host_done_value = ++h->regen_seq[l];
-    CK(ffmp::launch_flow_field(fa, h->rg_grid, h->side[l]));
-    if (tev) CK(cudaEventRecord(tev[3], h->side[l]));
-    h->launches += 1;
-    CK(cudaEventRecord(h->ev_regen[l], h->side[l]));
-    h->regen_pending[l] = true;
-    h->step_index += 1;
-    return FFMP_OK;
+    if (!last) {
+        h->group_open = true;
+        h->step_index += 1;
+        if (tev) h->tev_regen[h->timing_n - 1] = false;
+        return FFMP_OK;
+    }
+    if (tev) h->tev_regen[h->timing_n - 1] = true;
+    return launch_regen(h, st, tev);
 }
 
 }  // namespace
@@ -291,9 +338,11 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
     h->cfg = *cfg;
     if (const char *f = std::getenv("FFMP_STEP_FUSED")) h->fused = std::atoi(f) != 0;
     if (const char *f = std::getenv("FFMP_HOST_IO")) h->host_io = std::atoi(f);
+    if (const char *f = std::getenv("FFMP_TICK_PDL")) h->tick_pdl = std::atoi(f) != 0;
     if (const char *f = std::getenv("FFMP_HOST_IO_STATS")) h->io_stats = std::atoi(f) != 0;
     h->ws = workspace_layout(cfg);
-    h->nlist = cfg->slots - 1;
+    h->batch = regen_batch_of(cfg);
+    h->nlist = (cfg->slots - 1) / h->batch;
     std::memset(&h->b, 0, sizeof(h->b));
     for (int i = 0; i < MAX_LISTS; ++i) { h->side[i] = nullptr; h->ev_step[i] = nullptr; h->ev_regen[i] = nullptr; h->regen_pending[i] = false; h->regen_seq[i] = 0; }
     std::memset(h->tev, 0, sizeof(h->tev));
@@ -325,9 +374,7 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
     }
     const int maxg = ffmp::flow_field_max_grid(cfg->grid);
     h->ff_grid = cfg->num_envs < maxg ? cfg->num_envs : maxg;
-    int rg = REGEN_GRID;
-    if (const char *e = std::getenv("FFMP_REGEN_GRID")) { const int v = std::atoi(e); if (v >= 1 && v <= REGEN_GRID) rg = v; }   // development switch
-    h->rg_grid = cfg->num_envs < rg ? cfg->num_envs : rg;
+    h->rg_grid = regen_grid_of(cfg);
     *out = h;
     return FFMP_OK;
 }
@@ -430,6 +477,7 @@ int ffmp_reset(ffmp_handle *h, const uint8_t *mask_dev, void *stream) {
     }
     h->p = 1;
     h->step_index = 0;
+    h->group_open = false;
     ffmp::StepArgs a = step_args(h);
     a.mode = 2; a.slot_new = 1; a.write_older = 1;
     a.regen_env = h->list_env(0); a.regen_episode = h->list_episode(0); a.regen_count = h->list_count(0);
@@ -603,17 +651,22 @@ int ffmp_timing(ffmp_handle *h, int32_t enable, float *tick_ms, float *regen_ms,
     }
     h->timing = false;
     double d = 0, o = 0;
+    int regens = 0;
     for (int i = 0; i < h->timing_n; ++i) {
         float a = 0, b = 0;
         CK(cudaEventSynchronize(h->tev[i][1]));
-        CK(cudaEventSynchronize(h->tev[i][3]));
         CK(cudaEventElapsedTime(&a, h->tev[i][0], h->tev[i][1]));
-        CK(cudaEventElapsedTime(&b, h->tev[i][2], h->tev[i][3]));
-        d += a; o += b;
+        d += a;
+        if (h->tev_regen[i]) {
+            CK(cudaEventSynchronize(h->tev[i][3]));
+            CK(cudaEventElapsedTime(&b, h->tev[i][2], h->tev[i][3]));
+            o += b;
+            regens += 1;
+        }
     }
     const int n = h->timing_n > 0 ? h->timing_n : 1;
     if (tick_ms) *tick_ms = static_cast<float>(d / n);
-    if (regen_ms) *regen_ms = static_cast<float>(o / n);
+    if (regen_ms) *regen_ms = static_cast<float>(o / (regens > 0 ? regens : 1));   // average per regeneration launch
     if (ticks) *ticks = h->timing_n;
     h->timing_n = 0;
     return FFMP_OK;
@@ -891,6 +944,8 @@ int ffmp_feed_destroy(ffmp_feed *f) {
 int ffmp_join(ffmp_handle *h, void *stream) {
     if (!h) return fail(FFMP_ERR_ARG, "handle is null");
     DeviceGuard guard(h->cfg.device);
+    // episode ends of an unfinished group of ticks (regen_batch > 1) are handed to the regeneration now
+    if (h->group_open) if (int rc = launch_regen(h, static_cast<cudaStream_t>(stream), nullptr)) return rc;
     for (int l = 0; l < h->nlist; ++l)
         if (h->regen_pending[l]) CK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), h->ev_regen[l], 0));
     return FFMP_OK;

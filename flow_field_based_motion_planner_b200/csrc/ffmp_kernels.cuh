@@ -143,7 +143,7 @@ cudaError_t launch_flow_order(const int32_t *goal_cells, int n, int G, uint32_t 
 // tmap: TMA descriptor of the flow planes [S*N][G][G] (box W x ceil16(W)) or null -> plain-load observe kernel
 // fused: run the scalar step inside the TMA observe kernel (one launch per tick); ignored without a tensor map
 cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t st, cudaEvent_t between = nullptr,
-                        bool fused = true);
+                        bool fused = true, bool pdl = false);
 cudaError_t launch_rewarder(const RewarderArgs &a, cudaStream_t st);
 cudaError_t launch_terminal_obs(const StepArgs &a, cudaStream_t st);      // step.cu: behind a mode-0 step when term_frames is set
 int flow_field_max_grid(int G);            // resident CTAs for a full wave (multiple of the SM count)

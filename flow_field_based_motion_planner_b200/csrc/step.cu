@@ -527,6 +527,9 @@ __global__ void __launch_bounds__(128) tick_tma_kernel(const __grid_constant__ C
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
+        // when this tick was launched as a programmatic dependent of the previous one its CTAs are resident early and
+        // wait here for the previous grid (returns at once otherwise)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         uint32_t *st = a.state + static_cast<size_t>(e) * ST_WORDS;
         const uint4 s0 = *reinterpret_cast<const uint4 *>(st);        // x y yaw gx
         const uint4 s1 = *reinterpret_cast<const uint4 *>(st + 4);    // gy d_first return steps
@@ -776,7 +779,7 @@ static cudaError_t opt_in_shared(size_t smem) {
     return ce;
 }
 
-cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t st, cudaEvent_t between, bool fused) {
+cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t st, cudaEvent_t between, bool fused, bool pdl) {
     if (a.N <= 0) return cudaSuccess;
     const size_t smem = tmap ? static_cast<size_t>((a.W + 30) & ~15) * a.W + 16 : 0;
     if (tmap) {
@@ -785,11 +788,20 @@ cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t
             if (ce != cudaSuccess) return ce;
         }
         if (fused && !between) {
-            if (a.trace) tick_tma_kernel<true, 0><<<a.N, 128, smem, st>>>(*tmap, a);
-            else if (a.W == 100) tick_tma_kernel<false, 100><<<a.N, 128, smem, st>>>(*tmap, a);   // the reference's window
-            else if (a.W == 64) tick_tma_kernel<false, 64><<<a.N, 128, smem, st>>>(*tmap, a);     // BASELINE config 2
-            else tick_tma_kernel<false, 0><<<a.N, 128, smem, st>>>(*tmap, a);   // the whole tick in one kernel
-            return cudaGetLastError();
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(static_cast<unsigned>(a.N));
+            cfg.blockDim = dim3(128);
+            cfg.stream = st;
+            cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = pdl ? 1 : 0;
+            if (a.trace) return cudaLaunchKernelEx(&cfg, tick_tma_kernel<true, 0>, *tmap, a);
+            if (a.W == 100) return cudaLaunchKernelEx(&cfg, tick_tma_kernel<false, 100>, *tmap, a);   // the reference's window
+            if (a.W == 64) return cudaLaunchKernelEx(&cfg, tick_tma_kernel<false, 64>, *tmap, a);     // BASELINE config 2
+            return cudaLaunchKernelEx(&cfg, tick_tma_kernel<false, 0>, *tmap, a);   // the whole tick in one kernel
         }
     }
     dynamics_kernel<<<(a.N + 127) / 128, 128, 0, st>>>(a);

@@ -30,7 +30,7 @@ class Cfg(C.Structure):
         ("abi_version", C.c_uint32), ("device", C.c_int32), ("num_envs", C.c_int32), ("grid", C.c_int32),
         ("window", C.c_int32), ("ring", C.c_int32), ("slots", C.c_int32), ("max_steps", C.c_int32),
         ("goal_mode", C.c_int32), ("block_shift", C.c_int32), ("p_thresh", C.c_uint32), ("env_id_base", C.c_uint32),
-        ("seed", C.c_uint64), ("dt", C.c_float), ("reserved", C.c_uint32),
+        ("seed", C.c_uint64), ("dt", C.c_float), ("regen_batch", C.c_uint32),
     ]
 
 

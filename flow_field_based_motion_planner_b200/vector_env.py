@@ -39,7 +39,8 @@ class FFMPConfig:
     grid: int = 128                 # G
     window: int = MAP_GRID_NUM      # W (local map side)
     ring: int = 8                   # K observation frame slots (2 = contiguous [N,2,W,W])
-    slots: int = 8                  # S resident scenario slots per env (S-1 regenerations in flight; 2..16)
+    slots: int = 8                  # S resident scenario slots per env (2..16)
+    regen_batch: int = 0            # ticks per background regeneration launch (0 = library default, see ffmp_b200.h)
     max_steps: int = MAX_STEPS
     goal_mode: int = 0              # 0 re-sampled per episode, 1 static at (G-8, G-8)
     block_shift: int = 3
@@ -92,7 +93,7 @@ class FFMPVectorEnv:
         c = native.Cfg(abi_version=native.ABI_VERSION, device=dev_index, num_envs=cfg.num_envs, grid=cfg.grid,
                        window=cfg.window, ring=cfg.ring, slots=cfg.slots, max_steps=cfg.max_steps,
                        goal_mode=cfg.goal_mode, block_shift=cfg.block_shift, p_thresh=p_threshold(cfg.p_occ),
-                       env_id_base=cfg.env_id_base, seed=cfg.seed, dt=cfg.dt, reserved=0)
+                       env_id_base=cfg.env_id_base, seed=cfg.seed, dt=cfg.dt, regen_batch=cfg.regen_batch)
         self._cfg = c
         sz = native.Sizes()
         native.check(self._L.ffmp_query_sizes(C.byref(c), C.byref(sz)), "ffmp_query_sizes")

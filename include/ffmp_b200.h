@@ -59,7 +59,9 @@ typedef struct ffmp_cfg {
     uint32_t env_id_base;  /* global id of local env 0 (multi-GPU sharding) */
     uint64_t seed;
     float dt;              /* integration step [s] */
-    uint32_t reserved;
+    uint32_t regen_batch;  /* ticks per background regeneration launch: 0 = library default (max(1, min(4, (S-1)/5))), else
+                              1..min(8, S-1).  The episode ends of m consecutive ticks share one list and one launch, and the
+                              S-1 ticks of slack are split over floor((S-1)/m) lists; the step results do not depend on it */
 } ffmp_cfg;
 
 /* Byte sizes of every caller-allocated buffer for a given cfg (ffmp_query_sizes). */

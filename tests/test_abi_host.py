@@ -41,12 +41,12 @@ def test_cfg_validation_without_gpu():
     L = native.lib()
     sz = native.Sizes()
     good = dict(abi_version=1, device=0, num_envs=8, grid=128, window=100, ring=8, slots=3, max_steps=200,
-                goal_mode=0, block_shift=3, p_thresh=1, env_id_base=0, seed=0, dt=0.1, reserved=0)
+                goal_mode=0, block_shift=3, p_thresh=1, env_id_base=0, seed=0, dt=0.1, regen_batch=0)
     assert L.ffmp_query_sizes(C.byref(native.Cfg(**good)), C.byref(sz)) == 0
     assert sz.flow == 3 * 8 * 128 * 128 and sz.cost == 4 * sz.flow and sz.frames == 8 * 8 * 100 * 100
     assert sz.state == 8 * 64 and sz.scen == 3 * 8 * 32 and sz.workspace > 0
     for key, bad in [("abi_version", 2), ("num_envs", 0), ("grid", 130), ("grid", 8), ("window", 102), ("ring", 1),
-                     ("slots", 1), ("max_steps", 0), ("goal_mode", 2), ("dt", 0.0), ("grid", 1024), ("grid", 144)]:
+                     ("slots", 1), ("regen_batch", 3), ("regen_batch", 9), ("max_steps", 0), ("goal_mode", 2), ("dt", 0.0), ("grid", 1024), ("grid", 144)]:
         rc = L.ffmp_query_sizes(C.byref(native.Cfg(**{**good, key: bad})), C.byref(sz))
         assert rc < 0, key
         assert len(L.ffmp_last_error()) > 0
@@ -59,7 +59,7 @@ def test_fails_loudly_without_gpu():
     L = native.lib()
     h = C.c_void_p()
     cfg = native.Cfg(abi_version=1, device=0, num_envs=8, grid=128, window=100, ring=8, slots=3, max_steps=200,
-                     goal_mode=0, block_shift=3, p_thresh=1, env_id_base=0, seed=0, dt=0.1, reserved=0)
+                     goal_mode=0, block_shift=3, p_thresh=1, env_id_base=0, seed=0, dt=0.1, regen_batch=0)
     assert L.ffmp_create(C.byref(cfg), C.byref(h)) == -2          # FFMP_ERR_DEVICE: no CPU fallback
     assert b"no CUDA device" in L.ffmp_last_error()
     with pytest.raises(native.NativeError):

@@ -247,6 +247,31 @@ def test_rollout_ring_and_slot_variants(ffmp, ring, slots):
         rollout_parity(ffmp, 32, 60, seed=8, grid=64, window=32, ring=ring, slots=slots, max_steps=12, check_every=30, terminal_obs=False)
 
 
+@pytest.mark.parametrize("slots,batch", [(12, 2), (8, 3), (4, 3), (16, 5), (5, 2)])
+def test_rollout_grouped_regeneration(ffmp, cuda_device, slots, batch):
+    """ffmp_cfg.regen_batch: the episode ends of `batch` consecutive ticks share one regeneration list and launch (and the
+    ticks in between start as programmatic dependents of each other).  Results must not depend on the grouping: stepwise
+    against the oracle with short episodes, then open-loop rollouts whose lengths leave groups unfinished at the joins."""
+    kw = dict(grid=64, window=32, slots=slots, regen_batch=batch, max_steps=6)
+    rollout_parity(ffmp, 32, 90, seed=17, check_every=31, terminal_obs=False, **kw)
+    rollout_parity(ffmp, 24, 40, seed=18, check_every=13, p_occ=0.3, block_shift=0, **{**kw, "grid": 128, "window": 100})
+    N = 48
+    env = ffmp.FFMPVectorEnv(N, seed=19, **kw)
+    orc = oracle.OracleVectorEnv(N, seed=19, grid=64, window=32, max_steps=6)
+    env.reset(); orc.reset()
+    rng = np.random.default_rng(3)
+    done_total = 0
+    for T in (1, 7, 40, 2 * batch, 2 * batch + 1, 33):
+        acts = rng.integers(0, 28, (T, N))
+        env.rollout(torch.as_tensor(acts, device=cuda_device))
+        for t in range(T):
+            orc.step(acts[t])
+            done_total += int(orc.done.sum())
+        compare_env(env, orc, T, check_planes=True)
+    assert done_total > 8 * N and env.error_word() == 0
+    env.close()
+
+
 def test_rollout_dense_obstacles_short_episodes(ffmp):
     """p=0.3 per-cell noise: episodes of a few steps, so nearly every step regenerates slots."""
     rollout_parity(ffmp, 32, 200, seed=9, grid=128, window=100, p_occ=0.3, block_shift=0, check_every=50)
