@@ -110,6 +110,48 @@ int regen_grid_of(const ffmp_cfg *c) {
     return c->num_envs < g ? c->num_envs : g;
 }
 
+// Experiment (FFMP_REGEN_SMS): `n` non-blocking streams of a green context that owns `sms` SMs (rounded by the driver).
+// Returns the SM count of the partition, 0 when green contexts are not available (the caller then makes plain streams).
+int green_streams(int device, int sms, int n, cudaStream_t *out, void **ctx_out) {
+    typedef CUresult (*GetRes)(CUdevice, CUdevResource *, CUdevResourceType);
+    typedef CUresult (*Split)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int);
+    typedef CUresult (*GenDesc)(CUdevResourceDesc *, CUdevResource *, unsigned int);
+    typedef CUresult (*Create)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int);
+    typedef CUresult (*StreamCreate)(CUstream *, CUgreenCtx, unsigned int, int);
+    typedef CUresult (*DevGet)(CUdevice *, int);
+    auto sym = [](const char *name) -> void * {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+        return fn;
+    };
+    GetRes get_res = reinterpret_cast<GetRes>(sym("cuDeviceGetDevResource"));
+    Split split = reinterpret_cast<Split>(sym("cuDevSmResourceSplitByCount"));
+    GenDesc gen = reinterpret_cast<GenDesc>(sym("cuDevResourceGenerateDesc"));
+    Create create = reinterpret_cast<Create>(sym("cuGreenCtxCreate"));
+    StreamCreate screate = reinterpret_cast<StreamCreate>(sym("cuGreenCtxStreamCreate"));
+    DevGet dev_get = reinterpret_cast<DevGet>(sym("cuDeviceGet"));
+    if (!get_res || !split || !gen || !create || !screate || !dev_get) return 0;
+    CUdevice dev;
+    CUdevResource all, part, rem;
+    unsigned int groups = 1;
+    CUdevResourceDesc desc;
+    CUgreenCtx g;
+    if (dev_get(&dev, device) != CUDA_SUCCESS) return 0;
+    if (get_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return 0;
+    if (split(&part, &groups, &all, &rem, 0, static_cast<unsigned int>(sms)) != CUDA_SUCCESS || groups < 1) return 0;
+    if (gen(&desc, &part, 1) != CUDA_SUCCESS) return 0;
+    if (create(&g, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return 0;
+    for (int i = 0; i < n; ++i) {
+        CUstream st = nullptr;
+        if (screate(&st, g, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return 0;
+        out[i] = st;
+    }
+    *ctx_out = g;
+    std::fprintf(stderr, "[ffmp] regeneration streams on a green context with %u of %u SMs\n", part.sm.smCount, all.sm.smCount);
+    return static_cast<int>(part.sm.smCount);
+}
+
 struct Workspace {
     size_t error_word, lists, actions, obs_order, hi, total;
     size_t list_stride;  // bytes per regen list block: [count,ticket,pad..256B][env u32 m*N][episode u32 m*N]
@@ -153,6 +195,7 @@ struct ffmp_handle {
     int rg_grid = 0;                // background regeneration grid (few items per tick)
     CUtensorMap tmap;               // flow planes as a 3-D u8 tensor for the TMA observe kernel
     bool use_tma = false;
+    void *green = nullptr;          // experiment: green context of the regeneration streams
     bool tick_pdl = true;           // step kernels launched with the programmatic-dependent attribute (FFMP_TICK_PDL=0: off)
     bool fused = true;              // one kernel per tick (env FFMP_STEP_FUSED=0 selects dynamics + observe kernels)
     // optional per-kernel timing (ffmp_timing): events [before tick, after tick] on the caller's stream and
@@ -347,8 +390,11 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
     for (int i = 0; i < MAX_LISTS; ++i) { h->side[i] = nullptr; h->ev_step[i] = nullptr; h->ev_regen[i] = nullptr; h->regen_pending[i] = false; h->regen_seq[i] = 0; }
     std::memset(h->tev, 0, sizeof(h->tev));
     cudaError_t ce = cudaSuccess;
+    int regen_sms = 0;
+    if (const char *e = std::getenv("FFMP_REGEN_SMS")) regen_sms = std::atoi(e);     // experiment: regeneration confined to an SM partition
+    if (regen_sms > 0) regen_sms = green_streams(cfg->device, regen_sms, h->nlist, h->side, &h->green);
     for (int i = 0; i < h->nlist && ce == cudaSuccess; ++i) {
-        ce = cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking);
+        if (!h->side[i]) ce = cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_step[i], cudaEventDisableTiming);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_regen[i], cudaEventDisableTiming);
     }
