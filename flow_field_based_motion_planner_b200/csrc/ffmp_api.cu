@@ -7,6 +7,7 @@
 #include <ctime>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/ffmp_b200.h"
 #include "ffmp_kernels.cuh"
@@ -110,48 +111,6 @@ int regen_grid_of(const ffmp_cfg *c) {
     return c->num_envs < g ? c->num_envs : g;
 }
 
-// Experiment (FFMP_REGEN_SMS): `n` non-blocking streams of a green context that owns `sms` SMs (rounded by the driver).
-// Returns the SM count of the partition, 0 when green contexts are not available (the caller then makes plain streams).
-int green_streams(int device, int sms, int n, cudaStream_t *out, void **ctx_out) {
-    typedef CUresult (*GetRes)(CUdevice, CUdevResource *, CUdevResourceType);
-    typedef CUresult (*Split)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int);
-    typedef CUresult (*GenDesc)(CUdevResourceDesc *, CUdevResource *, unsigned int);
-    typedef CUresult (*Create)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int);
-    typedef CUresult (*StreamCreate)(CUstream *, CUgreenCtx, unsigned int, int);
-    typedef CUresult (*DevGet)(CUdevice *, int);
-    auto sym = [](const char *name) -> void * {
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
-        return fn;
-    };
-    GetRes get_res = reinterpret_cast<GetRes>(sym("cuDeviceGetDevResource"));
-    Split split = reinterpret_cast<Split>(sym("cuDevSmResourceSplitByCount"));
-    GenDesc gen = reinterpret_cast<GenDesc>(sym("cuDevResourceGenerateDesc"));
-    Create create = reinterpret_cast<Create>(sym("cuGreenCtxCreate"));
-    StreamCreate screate = reinterpret_cast<StreamCreate>(sym("cuGreenCtxStreamCreate"));
-    DevGet dev_get = reinterpret_cast<DevGet>(sym("cuDeviceGet"));
-    if (!get_res || !split || !gen || !create || !screate || !dev_get) return 0;
-    CUdevice dev;
-    CUdevResource all, part, rem;
-    unsigned int groups = 1;
-    CUdevResourceDesc desc;
-    CUgreenCtx g;
-    if (dev_get(&dev, device) != CUDA_SUCCESS) return 0;
-    if (get_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return 0;
-    if (split(&part, &groups, &all, &rem, 0, static_cast<unsigned int>(sms)) != CUDA_SUCCESS || groups < 1) return 0;
-    if (gen(&desc, &part, 1) != CUDA_SUCCESS) return 0;
-    if (create(&g, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return 0;
-    for (int i = 0; i < n; ++i) {
-        CUstream st = nullptr;
-        if (screate(&st, g, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return 0;
-        out[i] = st;
-    }
-    *ctx_out = g;
-    std::fprintf(stderr, "[ffmp] regeneration streams on a green context with %u of %u SMs\n", part.sm.smCount, all.sm.smCount);
-    return static_cast<int>(part.sm.smCount);
-}
-
 struct Workspace {
     size_t error_word, lists, actions, obs_order, hi, total;
     size_t list_stride;  // bytes per regen list block: [count,ticket,pad..256B][env u32 m*N][episode u32 m*N]
@@ -195,7 +154,6 @@ struct ffmp_handle {
     int rg_grid = 0;                // background regeneration grid (few items per tick)
     CUtensorMap tmap;               // flow planes as a 3-D u8 tensor for the TMA observe kernel
     bool use_tma = false;
-    void *green = nullptr;          // experiment: green context of the regeneration streams
     bool tick_pdl = true;           // step kernels launched with the programmatic-dependent attribute (FFMP_TICK_PDL=0: off)
     bool fused = true;              // one kernel per tick (env FFMP_STEP_FUSED=0 selects dynamics + observe kernels)
     // optional per-kernel timing (ffmp_timing): events [before tick, after tick] on the caller's stream and
@@ -219,6 +177,15 @@ struct ffmp_handle {
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double acc8 = 0;
     uint64_t acc_n = 0;
+    // ffmp_rollout_graphed: instantiated CUDA graphs of T-tick rollouts, keyed by what is baked into their nodes
+    struct RolloutGraph {
+        const int64_t *actions; int32_t T; int p0; int list0; const uint8_t *term;   // key
+        cudaGraphExec_t exec; int p1; uint64_t ticks; uint64_t launches; uint64_t stamp;
+    };
+    std::vector<RolloutGraph> graphs;
+    uint64_t graph_stamp = 0;
+    bool capturing = false;
+    cudaStream_t cap_stream = nullptr;     // origin stream of the captures
     uint8_t *term_frames = nullptr;        // caller's [N][2][W][W] buffer (ffmp_set_terminal_obs) or null
     int32_t *term_order = nullptr;         // library-owned [N][8] (allocated with the first ffmp_set_terminal_obs)
     unsigned long long *trace = nullptr;   // FFMP_TRACE=1: [N][8] tick-kernel timestamps (library-owned, diagnostics only)
@@ -303,7 +270,7 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
         // (the usual case when the caller synchronises every step) no device-side wait is queued in front of the tick.
         // The regeneration kernel's last CTA publishes its launch number in mapped host memory: one plain load tells whether
         // the launch has completed (a cudaEventQuery costs 1.7 us of host time in front of the step kernel's launch).
-        if (h->flag_host[16 + l] != h->regen_seq[l]) CK(cudaStreamWaitEvent(st, h->ev_regen[l], 0));
+        if (h->capturing || h->flag_host[16 + l] != h->regen_seq[l]) CK(cudaStreamWaitEvent(st, h->ev_regen[l], 0));
         h->regen_pending[l] = false;
     }
     if (h->io_stats) h->t_evq = now_us();
@@ -345,6 +312,19 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
     }
     if (tev) h->tev_regen[h->timing_n - 1] = true;
     return launch_regen(h, st, tev);
+}
+
+void drop_graphs(ffmp_handle *h) {
+    for (auto &g : h->graphs) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+}
+
+// Flush an unfinished group and order `st` after every queued regeneration; later work on `st` needs no further waits.
+int join_and_clear(ffmp_handle *h, cudaStream_t st) {
+    if (h->group_open) if (int rc = launch_regen(h, st, nullptr)) return rc;
+    for (int l = 0; l < h->nlist; ++l)
+        if (h->regen_pending[l]) { CK(cudaStreamWaitEvent(st, h->ev_regen[l], 0)); h->regen_pending[l] = false; }
+    return FFMP_OK;
 }
 
 }  // namespace
@@ -390,11 +370,8 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
     for (int i = 0; i < MAX_LISTS; ++i) { h->side[i] = nullptr; h->ev_step[i] = nullptr; h->ev_regen[i] = nullptr; h->regen_pending[i] = false; h->regen_seq[i] = 0; }
     std::memset(h->tev, 0, sizeof(h->tev));
     cudaError_t ce = cudaSuccess;
-    int regen_sms = 0;
-    if (const char *e = std::getenv("FFMP_REGEN_SMS")) regen_sms = std::atoi(e);     // experiment: regeneration confined to an SM partition
-    if (regen_sms > 0) regen_sms = green_streams(cfg->device, regen_sms, h->nlist, h->side, &h->green);
     for (int i = 0; i < h->nlist && ce == cudaSuccess; ++i) {
-        if (!h->side[i]) ce = cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking);
+        ce = cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_step[i], cudaEventDisableTiming);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_regen[i], cudaEventDisableTiming);
     }
@@ -438,6 +415,7 @@ int ffmp_bind(ffmp_handle *h, const ffmp_buffers *bufs) {
                                  reinterpret_cast<uintptr_t>(bufs->workspace)};
     for (uintptr_t p : aligned)
         if (p % 16) return fail(FFMP_ERR_ARG, "plane / frame / state / workspace buffers must be 16-byte aligned");
+    drop_graphs(h);
     h->b = *bufs;
     h->bound = true;
     h->ready = false;
@@ -489,6 +467,8 @@ int ffmp_destroy(ffmp_handle *h) {
                      static_cast<unsigned long long>(h->acc_n), h->acc[0] / n, h->acc[1] / n, h->acc[2] / n, h->acc[3] / n,
                      h->acc[4] / n, h->acc[5] / n);
     }
+    drop_graphs(h);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     if (h->trace) cudaFree(h->trace);
     if (h->term_order) cudaFree(h->term_order);
     if (h->flag_host) cudaFreeHost(const_cast<uint32_t *>(h->flag_host));
@@ -538,6 +518,64 @@ int ffmp_step(ffmp_handle *h, const int64_t *actions_dev, void *stream) {
     if (!h->ready) return fail(FFMP_ERR_STATE, "ffmp_reset must be called before ffmp_step");
     DeviceGuard guard(h->cfg.device);
     return run_tick(h, 0, actions_dev, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int ffmp_rollout_graphed(ffmp_handle *h, const int64_t *actions_dev, int32_t T, void *stream) {
+    if (!h || !actions_dev || T < 0) return fail(FFMP_ERR_ARG, "bad argument");
+    if (!h->ready) return fail(FFMP_ERR_STATE, "ffmp_reset must be called before ffmp_rollout_graphed");
+    if (T == 0) return FFMP_OK;
+    if (h->timing || h->trace || h->wait_mode) return ffmp_rollout(h, actions_dev, T, stream);   // diagnostics modes: plain launches
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (int rc = join_and_clear(h, st)) return rc;
+    const int list0 = static_cast<int>((h->step_index / static_cast<uint64_t>(h->batch)) % static_cast<uint64_t>(h->nlist));
+    ffmp_handle::RolloutGraph *g = nullptr;
+    for (auto &c : h->graphs)
+        if (c.actions == actions_dev && c.T == T && c.p0 == h->p && c.list0 == list0 && c.term == h->term_frames) g = &c;
+    if (!g) {
+        // capture the T ticks with their regeneration launches (side streams fork from and join back into `st`)
+        const uint64_t launches0 = h->launches, ticks0 = h->step_index;
+        const int p0 = h->p;
+        // (on a stream of the library: the caller's may be the legacy default stream, which cannot be captured)
+        if (!h->cap_stream) CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+        cudaStream_t cs = h->cap_stream;
+        CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+        h->capturing = true;
+        int rc = FFMP_OK;
+        for (int32_t t = 0; t < T && rc == FFMP_OK; ++t)
+            rc = run_tick(h, 0, actions_dev + static_cast<size_t>(t) * h->cfg.num_envs, nullptr, cs);
+        if (rc == FFMP_OK) rc = join_and_clear(h, cs);
+        h->capturing = false;
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        if (rc != FFMP_OK || ce != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            for (int l = 0; l < h->nlist; ++l) h->regen_pending[l] = false;
+            h->ready = false;     // host-side counters advanced without the work having run: a full reset is required
+            return rc != FFMP_OK ? rc : fail(FFMP_ERR_CUDA, "stream capture of the rollout", ce);
+        }
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ci = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ci != cudaSuccess) { h->ready = false; return fail(FFMP_ERR_CUDA, "cudaGraphInstantiate", ci); }
+        if (h->graphs.size() >= 16) {     // evict the least recently used graph
+            size_t victim = 0;
+            for (size_t i = 1; i < h->graphs.size(); ++i) if (h->graphs[i].stamp < h->graphs[victim].stamp) victim = i;
+            cudaGraphExecDestroy(h->graphs[victim].exec);
+            h->graphs.erase(h->graphs.begin() + static_cast<long>(victim));
+        }
+        h->graphs.push_back({actions_dev, T, p0, list0, h->term_frames, exec, h->p, h->step_index - ticks0, h->launches - launches0, 0});
+        g = &h->graphs.back();
+        // the capture advanced the host-side state exactly as the replay below will
+        h->p = p0; h->step_index = ticks0; h->launches = launches0;
+    }
+    CK(cudaGraphLaunch(g->exec, st));
+    g->stamp = ++h->graph_stamp;
+    h->p = g->p1;
+    h->step_index += g->ticks;
+    h->launches += g->launches;
+    return FFMP_OK;
 }
 
 int ffmp_rollout(ffmp_handle *h, const int64_t *actions_dev, int32_t T, void *stream) {
@@ -735,6 +773,7 @@ int ffmp_set_terminal_obs(ffmp_handle *h, uint8_t *term_frames_dev) {
     if (term_frames_dev && !h->term_order)
         CK(cudaMalloc(&h->term_order, static_cast<size_t>(h->cfg.num_envs) * 8 * sizeof(int32_t)));
     h->term_frames = term_frames_dev;
+    drop_graphs(h);
     return FFMP_OK;
 }
 

@@ -13,7 +13,7 @@ COST_INF = 0x7FFFFFFF
 
 EXPORTS = [
     "ffmp_last_error", "ffmp_abi_version", "ffmp_query_sizes", "ffmp_create", "ffmp_bind", "ffmp_destroy",
-    "ffmp_reset", "ffmp_step", "ffmp_rollout", "ffmp_step_host", "ffmp_step_host_async", "ffmp_step_host_wait", "ffmp_obs_slot", "ffmp_set_obs_slot", "ffmp_set_terminal_obs", "ffmp_join", "ffmp_error_word", "ffmp_timing", "ffmp_launch_count", "ffmp_debug_trace", "ffmp_learner_input", "ffmp_scan", "ffmp_op_scan",
+    "ffmp_reset", "ffmp_step", "ffmp_rollout", "ffmp_rollout_graphed", "ffmp_step_host", "ffmp_step_host_async", "ffmp_step_host_wait", "ffmp_obs_slot", "ffmp_set_obs_slot", "ffmp_set_terminal_obs", "ffmp_join", "ffmp_error_word", "ffmp_timing", "ffmp_launch_count", "ffmp_debug_trace", "ffmp_learner_input", "ffmp_scan", "ffmp_op_scan",
     "ffmp_feed_create", "ffmp_feed_handle", "ffmp_feed_connect", "ffmp_feed_info", "ffmp_feed_push", "ffmp_feed_wait", "ffmp_feed_release", "ffmp_feed_error", "ffmp_feed_destroy", "ffmp_pack_transitions",
     "ffmp_op_scenarios", "ffmp_op_flow_field_workspace", "ffmp_op_flow_field", "ffmp_op_rewarder", "ffmp_op_rewarder2", "ffmp_op_reward_calculator",
     "ffmp_replay_gather",
@@ -70,6 +70,7 @@ def lib() -> C.CDLL:
     L.ffmp_reset.argtypes = [vp, vp, vp]
     L.ffmp_step.argtypes = [vp, vp, vp]
     L.ffmp_rollout.argtypes = [vp, vp, i32, vp]
+    L.ffmp_rollout_graphed.argtypes = [vp, vp, i32, vp]
     L.ffmp_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.ffmp_step_host_async.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.ffmp_step_host_wait.argtypes = [vp]

@@ -208,12 +208,21 @@ class FFMPVectorEnv:
     def decode_flags(flags):
         return {"is_collision": (flags & 1) != 0, "is_goal": (flags & 2) != 0, "truncated": (flags & 4) != 0}
 
-    def rollout(self, actions):
-        """actions int64[T,N] on the device: T back-to-back steps with no host work in between."""
-        a = actions.contiguous()
+    def rollout(self, actions, graph=False):
+        """actions int64[T,N] on the device: T back-to-back steps with no host work in between.  graph=True replays the T
+        steps as one CUDA graph launch (captured the first time this action buffer, T and ring phase are seen; the buffer's
+        contents are re-read by every replay, so refill it in place)."""
+        if not actions.is_contiguous():
+            if graph:
+                raise ValueError("rollout(graph=True) needs a contiguous action tensor (its address is part of the graph)")
+            actions = actions.contiguous()
+        a = actions
         assert a.dtype == torch.int64 and a.device == self.device and a.shape[1] == self.num_envs
+        fn = self._L.ffmp_rollout_graphed if graph else self._L.ffmp_rollout
         with torch.cuda.device(self.device):
-            native.check(self._L.ffmp_rollout(self._h, C.c_void_p(a.data_ptr()), int(a.shape[0]), self._stream()), "ffmp_rollout")
+            native.check(fn(self._h, C.c_void_p(a.data_ptr()), int(a.shape[0]), self._stream()), "ffmp_rollout")
+        if graph:
+            self._graph_actions = a          # keeps the captured buffer alive
         return self._obs(), self.reward, self._done_bool, self._info()
 
     def _host_buffers(self):

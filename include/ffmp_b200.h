@@ -119,6 +119,13 @@ int ffmp_step(ffmp_handle *h, const int64_t *actions_dev, void *stream);
 /* T back-to-back steps with actions_dev = i64[T][N]; identical to T ffmp_step calls. */
 int ffmp_rollout(ffmp_handle *h, const int64_t *actions_dev, int32_t T, void *stream);
 
+/* The same T steps replayed as ONE CUDA graph launch.  The first call for a given (actions_dev, T, ring phase, regeneration
+ * list phase) captures the T step kernels and their background regeneration launches (stream capture, side streams forked
+ * and joined), instantiates the graph and launches it; later calls with the same key only launch it (up to 16 graphs are
+ * kept, least recently used first out).  actions_dev must stay valid and is re-read by every replay.  A graph ends with
+ * the join of its regenerations, so `stream` needs no ffmp_join afterwards.  Results are identical to ffmp_rollout.    */
+int ffmp_rollout_graphed(ffmp_handle *h, const int64_t *actions_dev, int32_t T, void *stream);
+
 /* Host-buffer step (the reference-facing call with HOST memory): actions_host i64[N] in, reward f32[N], done u8[N],
  * flags u8[N], rel_goal f32[N][2] and velocity f32[N][2] out (any out pointer may be NULL); returns when the results are
  * in the host buffers.  The local_map observation stays on the device.

@@ -272,6 +272,39 @@ def test_rollout_grouped_regeneration(ffmp, cuda_device, slots, batch):
     env.close()
 
 
+@pytest.mark.parametrize("slots,batch,term", [(16, 0, False), (8, 0, True), (6, 2, False)])
+def test_rollout_graph_replay_matches_oracle(ffmp, cuda_device, slots, batch, term):
+    """ffmp_rollout_graphed: T ticks and their background regenerations captured once per (buffer, T, ring / list phase) and
+    replayed as one graph launch.  The action buffer is refilled in place between replays; phases cycle because T is not a
+    multiple of the ring or list periods; plain steps and plain rollouts are interleaved with the replays."""
+    N, T = 40, 10
+    kw = dict(grid=64, window=32, slots=slots, regen_batch=batch, max_steps=7)
+    env = ffmp.FFMPVectorEnv(N, seed=23, terminal_obs=term, **kw)
+    orc = oracle.OracleVectorEnv(N, seed=23, grid=64, window=32, max_steps=7)
+    env.reset(); orc.reset()
+    rng = np.random.default_rng(9)
+    buf = torch.zeros((T, N), dtype=torch.int64, device=cuda_device)
+    launches0 = env.launch_count()
+    for it in range(24):
+        acts = rng.integers(0, 28, (T, N))
+        buf.copy_(torch.as_tensor(acts, device=cuda_device))
+        env.rollout(buf, graph=True)
+        for t in range(T):
+            orc.step(acts[t])
+        compare_env(env, orc, it, check_planes=(it % 6 == 5))
+        if term and orc.done.any():
+            d = orc.done.astype(bool)
+            assert np.array_equal(t2n(env._info()["terminal_local_map"])[d], orc.term_local_map[d]), (it, "terminal_local_map")
+        if it % 5 == 4:           # plain calls in between shift the phases the next replays start from
+            a1 = rng.integers(0, 28, (3, N))
+            env.step(torch.as_tensor(a1[0], device=cuda_device)); orc.step(a1[0])
+            env.rollout(torch.as_tensor(a1[1:], device=cuda_device))
+            orc.step(a1[1]); orc.step(a1[2])
+            compare_env(env, orc, it, check_planes=True)
+    assert env.launch_count() - launches0 >= 24 * T and env.error_word() == 0
+    env.close()
+
+
 def test_rollout_dense_obstacles_short_episodes(ffmp):
     """p=0.3 per-cell noise: episodes of a few steps, so nearly every step regenerates slots."""
     rollout_parity(ffmp, 32, 200, seed=9, grid=128, window=100, p_occ=0.3, block_shift=0, check_every=50)

@@ -1,5 +1,7 @@
 """Experiment: background regeneration confined to an SM partition (green context, FFMP_REGEN_SMS) vs free to roam.
-Reports the device-resident rollout step and the host-buffer step of the bench workload."""
+Reports the device-resident rollout step and the host-buffer step of the bench workload.
+The switch lived in ffmp_create for this experiment only (commit 0e8fcc8; result: profiles/r02d_green_ctx_ab.txt, no gain) and
+is not in the library any more — check that commit out to re-run."""
 import json, os, subprocess, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if len(sys.argv) > 1 and sys.argv[1] == "child":
