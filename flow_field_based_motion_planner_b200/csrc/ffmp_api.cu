@@ -1064,9 +1064,8 @@ int ffmp_op_scenarios(int32_t device, int32_t n, int32_t G, uint32_t p_thresh, i
 size_t ffmp_op_flow_field_workspace(int32_t n, int32_t G) {
     if (n <= 0 || !ffmp::flow_field_supported(G)) return 0;
     const int maxg = ffmp::flow_field_max_grid(G);
-    // 256-byte header (work counter, completion ticket) + the per-CTA plane scratch + the hand-out order of the batch
-    return 256 + align_up(static_cast<size_t>(n < maxg ? n : maxg) * ffmp::flow_field_scratch_words(G) * 4, 256) +
-           static_cast<size_t>(n) * sizeof(uint32_t);
+    // 256-byte header (work counter, completion ticket) + the per-CTA plane scratch
+    return 256 + align_up(static_cast<size_t>(n < maxg ? n : maxg) * ffmp::flow_field_scratch_words(G) * 4, 256);
 }
 
 int ffmp_op_flow_field(int32_t device, int32_t n, int32_t G, const uint8_t *occ_dev, const int32_t *goal_cells_dev,
@@ -1089,13 +1088,6 @@ int ffmp_op_flow_field(int32_t device, int32_t n, int32_t G, const uint8_t *occ_
     a.hi_scratch = static_cast<uint32_t *>(workspace_dev) + 64;
     const int maxg = ffmp::flow_field_max_grid(G);
     const int grid = n < maxg ? n : maxg;
-    if (n >= 2 * grid) {
-        // several grids per warp / CTA: deepest grids first (flow_order.cu)
-        uint32_t *order = reinterpret_cast<uint32_t *>(static_cast<char *>(workspace_dev) + 256 +
-                                                       align_up(static_cast<size_t>(grid) * ffmp::flow_field_scratch_words(G) * 4, 256));
-        CK(ffmp::launch_flow_order(goal_cells_dev, n, G, order, st));
-        a.order = order;
-    }
     CK(ffmp::launch_flow_field(a, grid, st));
     return FFMP_OK;
 }

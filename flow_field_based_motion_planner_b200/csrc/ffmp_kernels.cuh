@@ -26,7 +26,6 @@ struct FlowArgs {
     const uint32_t *env_idx;    // dev u32[count] or null
     const uint32_t *episode;    // dev u32[count] or null (use episode_const; slot_mode only)
     const uint32_t *count_ptr;  // dev count or null
-    const uint32_t *order;      // dev u32[count] or null: hand-out position -> item (deepest grids first, see flow_order.cu)
     int count;
     uint32_t episode_const;
     int G, slot_mode, S, N;
@@ -139,7 +138,6 @@ cudaError_t launch_scan(const ScanArgs &a, cudaStream_t st);                // s
 cudaError_t launch_learner_input(const FeedArgs &a, cudaStream_t st);
 cudaError_t launch_scenarios(const ScenarioArgs &a, int grid, cudaStream_t st);
 cudaError_t launch_flow_field(const FlowArgs &a, int grid, cudaStream_t st);
-cudaError_t launch_flow_order(const int32_t *goal_cells, int n, int G, uint32_t *order, cudaStream_t st);   // flow_order.cu
 // tmap: TMA descriptor of the flow planes [S*N][G][G] (box W x ceil16(W)) or null -> plain-load observe kernel
 // fused: run the scalar step inside the TMA observe kernel (one launch per tick); ignored without a tensor map
 cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t st, cudaEvent_t between = nullptr,

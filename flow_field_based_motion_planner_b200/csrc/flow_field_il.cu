@@ -85,7 +85,6 @@ __global__ void __launch_bounds__(32, IL_WARPS_PER_SM) flow_field_il_kernel(Flow
             item = __shfl_sync(FULL, item, 0);
         }
         if (item >= count) break;
-        if (a.order) item = static_cast<int>(a.order[item]);
         const uint32_t env = a.env_idx ? a.env_idx[item] : static_cast<uint32_t>(item);
         const size_t cells = static_cast<size_t>(G) * G;
         size_t plane;

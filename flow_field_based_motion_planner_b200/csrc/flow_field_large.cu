@@ -101,7 +101,6 @@ __global__ void __launch_bounds__(32 * WPR, 1) flow_field_rows_kernel(FlowArgs a
             item = info.item;
         }
         if (item >= count) break;
-        if (a.order) item = static_cast<int>(a.order[item]);
         // ---- 0. item parameters ------------------------------------------------------------------------
         if (tid == 0) {
             const uint32_t env = a.env_idx ? a.env_idx[item] : static_cast<uint32_t>(item);

@@ -85,7 +85,6 @@ __global__ void __launch_bounds__(WD_T, 2) flow_field_wide_kernel(FlowArgs a) {
             item = info.item;
         }
         if (item >= count) break;
-        if (a.order) item = static_cast<int>(a.order[item]);
         if (tid == 0) {
             const uint32_t env = a.env_idx ? a.env_idx[item] : static_cast<uint32_t>(item);
             if (GEN) {

@@ -1,7 +1,8 @@
 """A/B timing of the flow-field operator on 4096 generated 128 x 128 maps (CUDA events, median of 7, 3 warm-ups).
     python tools/flow_ab.py            # runs the variants below, one subprocess each (the switches are read at first use)
     python tools/flow_ab.py child      # one measurement in this process
-Development switches: FFMP_FLOW_V2=1 = the round-1 kernel, FFMP_FLOW_CTAS = resident CTAs per SM of the launch."""
+AB_N / AB_G select the batch and the grid.  (History: profiles/r02a_flow_ab.txt = resident warps per SM, r02d_flow_order_ab.txt =
+deepest-first hand-out order against the natural order, which won and stayed.)"""
 import json, os, subprocess, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
@@ -43,7 +44,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
-        variants = [{"FFMP_FLOW_V2": "1"}, {}, {"FFMP_FLOW_NOORDER": "1"}] + [{"FFMP_FLOW_CTAS": str(c)} for c in (5, 6, 7, 8, 9)] + [{"FFMP_FLOW_CTAS": "8", "FFMP_FLOW_NOORDER": "1"}]
+        variants = []
+        for n in ("4096", "4096", "2048", "8192", "16384"):
+            variants += [{"AB_N": n}]
         for v in variants:
             env = dict(os.environ, **v)
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True)
