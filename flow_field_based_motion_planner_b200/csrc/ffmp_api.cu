@@ -154,6 +154,7 @@ struct ffmp_handle {
     int rg_grid = 0;                // background regeneration grid (few items per tick)
     CUtensorMap tmap;               // flow planes as a 3-D u8 tensor for the TMA observe kernel
     bool use_tma = false;
+    bool always_wait = false;       // FFMP_REGEN_WAIT=1: always queue the stream wait on the regeneration's event (see run_tick)
     bool tick_pdl = true;           // step kernels launched with the programmatic-dependent attribute (FFMP_TICK_PDL=0: off)
     bool fused = true;              // one kernel per tick (env FFMP_STEP_FUSED=0 selects dynamics + observe kernels)
     // optional per-kernel timing (ffmp_timing): events [before tick, after tick] on the caller's stream and
@@ -270,7 +271,11 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
         // (the usual case when the caller synchronises every step) no device-side wait is queued in front of the tick.
         // The regeneration kernel's last CTA publishes its launch number in mapped host memory: one plain load tells whether
         // the launch has completed (a cudaEventQuery costs 1.7 us of host time in front of the step kernel's launch).
-        if (h->capturing || h->flag_host[16 + l] != h->regen_seq[l]) CK(cudaStreamWaitEvent(st, h->ev_regen[l], 0));
+        // The skipped wait relies on this chain in the regeneration kernel: every CTA's stores, __threadfence, the ticket
+        // atomic; the last CTA's __threadfence_system, then the flag store; the host's load of the flag precedes the launch
+        // of the tick, whose loads are issued after kernel start (L1 invalidated).  FFMP_REGEN_WAIT=1 always queues the
+        // stream wait instead (the parity suite runs in both modes: test_rollout_with_regeneration_wait_forced).
+        if (h->capturing || h->always_wait || h->flag_host[16 + l] != h->regen_seq[l]) CK(cudaStreamWaitEvent(st, h->ev_regen[l], 0));
         h->regen_pending[l] = false;
     }
     if (h->io_stats) h->t_evq = now_us();
@@ -362,6 +367,7 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
     if (const char *f = std::getenv("FFMP_STEP_FUSED")) h->fused = std::atoi(f) != 0;
     if (const char *f = std::getenv("FFMP_HOST_IO")) h->host_io = std::atoi(f);
     if (const char *f = std::getenv("FFMP_TICK_PDL")) h->tick_pdl = std::atoi(f) != 0;
+    if (const char *f = std::getenv("FFMP_REGEN_WAIT")) h->always_wait = std::atoi(f) != 0;
     if (const char *f = std::getenv("FFMP_HOST_IO_STATS")) h->io_stats = std::atoi(f) != 0;
     h->ws = workspace_layout(cfg);
     h->batch = regen_batch_of(cfg);
@@ -415,6 +421,14 @@ int ffmp_bind(ffmp_handle *h, const ffmp_buffers *bufs) {
                                  reinterpret_cast<uintptr_t>(bufs->workspace)};
     for (uintptr_t p : aligned)
         if (p % 16) return fail(FFMP_ERR_ARG, "plane / frame / state / workspace buffers must be 16-byte aligned");
+    // the step kernels write the two-float records with one 8-byte store and the scalars with 4-byte stores
+    const void *pairs[] = {bufs->rel_goal, bufs->velocity, bufs->term_rel_goal, bufs->term_velocity};
+    for (const void *p : pairs)
+        if (reinterpret_cast<uintptr_t>(p) % 8)
+            return fail(FFMP_ERR_ARG, "rel_goal / velocity / term_rel_goal / term_velocity must be 8-byte aligned");
+    const void *words[] = {bufs->reward, bufs->fin_return, bufs->fin_length};
+    for (const void *p : words)
+        if (reinterpret_cast<uintptr_t>(p) % 4) return fail(FFMP_ERR_ARG, "reward / fin_return / fin_length must be 4-byte aligned");
     drop_graphs(h);
     h->b = *bufs;
     h->bound = true;

@@ -15,9 +15,12 @@ import torch
 import torch.distributed as dist
 
 
-def shard_range(global_envs: int, rank: int, world: int):
-    """Contiguous shard [lo, hi) of `global_envs` envs for `rank`; the first `global_envs % world` ranks get one more."""
+def shard_range(global_envs: int, rank: int, world: int, equal: bool = False):
+    """Contiguous shard [lo, hi) of `global_envs` envs for `rank`; the first `global_envs % world` ranks get one more.
+    equal=True raises instead: the learner feeds (all_gather_transitions, LearnerFeed) need the same N on every rank."""
     base, extra = divmod(global_envs, world)
+    if equal and extra:
+        raise ValueError(f"{global_envs} envs do not split evenly over {world} ranks (the learner feeds need equal shards)")
     lo = rank * base + min(rank, extra)
     return lo, lo + base + (1 if rank < extra else 0)
 
@@ -64,7 +67,8 @@ def unpack_transitions(buf, num_envs: int, window: int):
 
 def all_gather_transitions(obs, reward, done, window: int, group=None):
     """Every rank receives every shard's transition block, in rank order.  Returns (obs, reward, done) of the
-    global batch.  One all_gather_into_tensor of world * transition_nbytes bytes."""
+    global batch.  One all_gather_into_tensor of world * transition_nbytes bytes.  Every rank must hold the same number of
+    envs (shard_range(..., equal=True)): the collective needs equal sizes and the peers' blocks are decoded with the local n."""
     n = obs["local_map"].shape[0]
     local = pack_transitions(obs, reward, done)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
@@ -150,8 +154,12 @@ class LearnerFeed:
         native.check(self._L.ffmp_feed_handle(self._f, handle), "ffmp_feed_handle")
         handles = [bytes(handle)]
         if self.world > 1:
-            handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle), group=group)
+            both = [None] * self.world
+            dist.all_gather_object(both, (bytes(handle), self.N, self.W), group=group)
+            if any((n, w) != (self.N, self.W) for _, n, w in both):
+                raise ValueError(f"LearnerFeed needs the same num_envs / window on every rank, got {[(n, w) for _, n, w in both]} "
+                                 "(shard_range(..., equal=True))")
+            handles = [hb for hb, _, _ in both]
         for r, hb in enumerate(handles):
             if r != self.rank:
                 buf = (C.c_uint8 * 64).from_buffer_copy(hb)

@@ -103,6 +103,9 @@ uint32_t ffmp_abi_version(void);
 
 int ffmp_query_sizes(const ffmp_cfg *cfg, ffmp_sizes *out);
 int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out);
+/* Alignment (checked, FFMP_ERR_ARG otherwise): cost / flow / scen / state / frames / workspace 16 bytes; rel_goal / velocity /
+ * term_rel_goal / term_velocity 8 bytes (written as float2); reward / fin_return / fin_length 4 bytes.  A packed output block
+ * [reward f32 N | rel_goal f32 2N | velocity f32 2N | done u8 N | flags u8 N] therefore needs an even N.                 */
 int ffmp_bind(ffmp_handle *h, const ffmp_buffers *bufs);
 int ffmp_destroy(ffmp_handle *h);
 

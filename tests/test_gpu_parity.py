@@ -305,6 +305,14 @@ def test_rollout_graph_replay_matches_oracle(ffmp, cuda_device, slots, batch, te
     env.close()
 
 
+def test_rollout_with_regeneration_wait_forced(ffmp, monkeypatch):
+    """FFMP_REGEN_WAIT=1: the tick always waits on the regeneration's event instead of trusting the completion word in
+    mapped memory; same results either way."""
+    monkeypatch.setenv("FFMP_REGEN_WAIT", "1")
+    rollout_parity(ffmp, 32, 120, seed=27, grid=64, window=32, slots=3, max_steps=9, check_every=40)
+    rollout_parity(ffmp, 16, 60, seed=28, grid=128, window=100, slots=12, p_occ=0.3, block_shift=0, check_every=30)
+
+
 def test_rollout_dense_obstacles_short_episodes(ffmp):
     """p=0.3 per-cell noise: episodes of a few steps, so nearly every step regenerates slots."""
     rollout_parity(ffmp, 32, 200, seed=9, grid=128, window=100, p_occ=0.3, block_shift=0, check_every=50)
@@ -424,6 +432,17 @@ def test_invalid_actions_and_errors(ffmp, cuda_device):
     assert env.error_word() & 1
     with pytest.raises(ValueError):
         env.step(torch.zeros(5, dtype=torch.int64, device=cuda_device))
+    # ffmp_bind rejects output pointers the kernels' float2 / 4-byte stores cannot take
+    import ctypes as C
+    names = ("cost", "flow", "scen", "state", "frames", "rel_goal", "velocity", "reward", "done", "flags", "term_rel_goal",
+             "term_velocity", "fin_return", "fin_length")
+    ptrs = {n: getattr(env, n).data_ptr() for n in names}
+    L = ffmp.native.lib()
+    for bad, off in (("rel_goal", 4), ("term_velocity", 4), ("reward", 2), ("flow", 8)):
+        b = ffmp.native.Buffers(**{**ptrs, bad: ptrs[bad] + off}, workspace=env._workspace.data_ptr())
+        assert L.ffmp_bind(env._h, C.byref(b)) < 0 and b"aligned" in L.ffmp_last_error(), bad
+    b = ffmp.native.Buffers(**ptrs, workspace=env._workspace.data_ptr())
+    assert L.ffmp_bind(env._h, C.byref(b)) == 0
     env.close()
     with pytest.raises(ffmp.native.NativeError):
         ffmp.FFMPVectorEnv(4, grid=1024)                                        # unsupported in this build
@@ -750,11 +769,26 @@ def test_rollout_full_size_properties(ffmp, cuda_device):
     hi = ffmp.FFMPVectorEnv(N // 2, env_id_base=N // 2, **kw)
     for env in (full, lo, hi):
         env.reset()
+    # a strided sample of the 4096 envs against the oracle, bit for bit, at the full size (every random draw is keyed by the
+    # global env id, so a one-env oracle with env_id_base = id replays env `id` of the batch)
+    sample = [0, 1, 511, 1024, 2047, 2048, 3333, 4095]
+    orcs = [oracle.OracleVectorEnv(1, grid=128, window=100, seed=77, env_id_base=i) for i in sample]
+    for o in orcs:
+        o.reset()
+    sidx = torch.as_tensor(sample, device=cuda_device)
     gen = torch.Generator(device=cuda_device); gen.manual_seed(5)
     ends = 0
     for t in range(T):
         a = torch.randint(0, 28, (N,), generator=gen, device=cuda_device)
         obs, reward, done, info = full.step(a)
+        a_s = t2n(a[sidx])
+        for k, o in enumerate(orcs):
+            o.step(a_s[k:k + 1])
+        assert np.array_equal(t2n(reward[sidx]).view(np.uint32), np.concatenate([o.reward for o in orcs]).view(np.uint32)), (t, "sample reward")
+        assert np.array_equal(t2n(done[sidx]).astype(np.uint8), np.concatenate([o.done for o in orcs])), (t, "sample done")
+        assert np.array_equal(t2n(obs["relative_goal"][sidx]).view(np.uint32), np.concatenate([o.rel_goal for o in orcs]).view(np.uint32)), (t, "sample goal")
+        if t % 10 == 9:
+            assert np.array_equal(t2n(obs["local_map"][sidx]), np.concatenate([o.local_map for o in orcs])), (t, "sample local_map")
         o1, r1, d1, i1 = lo.step(a[:N // 2].contiguous())
         o2, r2, d2, i2 = hi.step(a[N // 2:].contiguous())
         assert torch.equal(reward.view(torch.int32), torch.cat([r1, r2]).view(torch.int32)), t
