@@ -357,11 +357,13 @@ def run_ours(a):
         dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * N * k2 / dt, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step * world,
                "d2h_bytes_per_step": env.d2h_bytes_per_step * world, "steps": k2,
-               "note": "FFMPVectorEnv.step_host every step, host buffers in and out: pinned int64 actions go in with one "
-                       "cudaMemcpyAsync, reward/done/flags/relative_goal/velocity are written into the caller's pinned block by "
-                       "a kernel queued behind the step, and the call returns when its completion word (mapped memory) is set: "
-                       "no device-to-host copy engine, no stream sync; the 20 KB/env local_map observations stay on the device "
-                       "for the learner"}
+               "note": "FFMPVectorEnv.step_host every step, host buffers in and out: the caller's pinned int64 actions are "
+                       "narrowed to one byte per env on the host and ride inside the step kernel's launch as a by-value "
+                       "parameter (up to 4096 envs per GPU; a cudaMemcpyAsync above that), reward/done/flags/relative_goal/velocity "
+                       "are written into the caller's pinned block by a kernel queued behind the step, and the call returns when "
+                       "its completion word (mapped memory) is set: no copy engine in either direction, no stream sync; "
+                       "h2d_bytes_per_step counts the caller's int64 buffer; the 20 KB/env local_map observations stay on the "
+                       "device for the learner"}
 
         # ---- steady state: the same step over a long window (the join of the last regeneration, ~50-90 us, is 15 % of a
         #      20-step window and < 0.5 % of this one) ----
@@ -487,6 +489,48 @@ def run_ours(a):
             sc_ms = x.elapsed_time(y) / 5
             extras["scan"] = {"beams": 360, "range_max_m": 3.5, "ms": sc_ms, "beams_per_s": N * 360 / (sc_ms * 1e-3)}
             del occ, scen, bufs, ws, sc_out
+
+            # ---- Q network forward (train.py:231-303) on the tcgen05 kernels: 256 observations straight
+            #      from learner_input's bf16 NCHW, random-init weights of the reference's shapes ----
+            if a.grid <= 128 and a.window == 100:
+                try:
+                    B = min(256, N)
+                    qn = ffmp.QNetwork(max_batch=B, device=str(dev))
+                    g = torch.Generator(device="cpu"); g.manual_seed(a.seed)
+                    sd = {}
+                    for name, shp in ffmp.qnet.SHAPES.items():
+                        fan_in = 1
+                        for d in shp[1:]:
+                            fan_in *= d
+                        sd[name + ".weight"] = (torch.rand(shp, generator=g) * 2 - 1) / math.sqrt(fan_in)
+                        sd[name + ".bias"] = (torch.rand(shp[0], generator=g) * 2 - 1) / math.sqrt(fan_in)
+                    qn.load_state_dict(sd)
+                    obs_m = env.learner_input(dtype=torch.bfloat16)[:B].contiguous()
+                    og, ov = env.rel_goal[:B].clone(), env.velocity[:B].clone()
+                    ot = torch.full((B, 1), 0.1, device=dev)
+                    qout = torch.empty((B, 28), device=dev)
+                    for _ in range(2):
+                        qn(obs_m, og, ov, ot, out=qout)
+                    torch.cuda.synchronize()
+                    x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    x.record()
+                    for _ in range(3):
+                        qn(obs_m, og, ov, ot, out=qout)
+                    y.record()
+                    torch.cuda.synchronize()
+                    q_ms = x.elapsed_time(y) / 3
+                    macs = (69 * 69 * 32 * 2048 + 38 * 38 * 64 * 32768 + 31 * 31 * 64 * 4096 + (24 * 24 + 17 * 17 + 100) * 64 * 4096
+                            + 6400 * 512 + 512 * 512 + 512 * 29)
+                    tfl = 2 * macs * B / (q_ms * 1e-3) / 1e12
+                    extras["qnet"] = {"kernel": "qnet_conv1_kernel + qnet_gemm_kernel (tcgen05 / TMEM / TMA)", "batch": B, "ms": q_ms,
+                                      "bound": "tensor", "achieved": tfl, "unit": "TFLOP/s", "dtype": "bf16 operands, f32 accumulate",
+                                      "peak": peaks.get("bf16_tflops_sustained"),
+                                      "frac": tfl / peaks["bf16_tflops_sustained"] if peaks.get("bf16_tflops_sustained") else None,
+                                      "gmac_per_sample": macs / 1e9, "finite": bool(torch.isfinite(qout).all().item())}
+                    qn.close()
+                    del qn, obs_m
+                except Exception as ex:      # a side measurement must not lose the headline line
+                    extras["qnet"] = {"error": repr(ex)[:200]}
 
     env.close()
     del env

@@ -169,6 +169,8 @@ struct ffmp_handle {
     volatile uint32_t *flag_host = nullptr;
     uint32_t *flag_dev = nullptr;
     uint32_t flag_seq = 0;
+    bool act_param = true;          // host-buffer steps of <= ACT_PARAM_MAX envs pass the actions inside the launch (FFMP_ACT_PARAM=0: copy them)
+    uint8_t act_bytes[ffmp::ACT_PARAM_MAX];
     int host_io = 1;                // FFMP_HOST_IO: 0 copy engines + stream sync, 1 mapped results (default), 2 mapped results + in-place actions
     int wait_mode = 0;              // what ffmp_step_host_wait has to do: 0 nothing, 1 spin on the flag, 2 synchronise wait_stream
     cudaStream_t wait_stream = nullptr;
@@ -238,7 +240,7 @@ ffmp::StepArgs step_args(const ffmp_handle *h) {
 
 // Queue the background regeneration of the current group's list (the episode ends of its ticks so far) behind the last
 // tick on `st`, and round the tick counter up to the next group.
-int launch_regen(ffmp_handle *h, cudaStream_t st, cudaEvent_t *tev) {
+int launch_regen(ffmp_handle *h, cudaStream_t st, cudaEvent_t *tev, bool flush = false) {
     const int l = static_cast<int>((h->step_index / static_cast<uint64_t>(h->batch)) % static_cast<uint64_t>(h->nlist));
     CK(cudaEventRecord(h->ev_step[l], st));
     CK(cudaStreamWaitEvent(h->side[l], h->ev_step[l], 0));
@@ -249,6 +251,7 @@ int launch_regen(ffmp_handle *h, cudaStream_t st, cudaEvent_t *tev) {
     fa.hi_scratch = h->hi_scratch() + (static_cast<size_t>(h->ff_grid) + static_cast<size_t>(l) * h->rg_grid) * ffmp::flow_field_scratch_words(h->cfg.grid);
     fa.host_done = h->flag_dev + 16 + l;
     fa.host_done_value = ++h->regen_seq[l];
+    fa.latency = flush ? 1 : 0;
     CK(ffmp::launch_flow_field(fa, h->rg_grid, h->side[l]));
     if (tev) CK(cudaEventRecord(tev[3], h->side[l]));
     h->launches += 1;
@@ -261,7 +264,7 @@ int launch_regen(ffmp_handle *h, cudaStream_t st, cudaEvent_t *tev) {
 
 // One env-step-like call (mode 0 step, mode 1 masked reset) with the background regeneration queued.
 int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *mask, cudaStream_t st,
-             const ffmp::HostExportArgs *host_export = nullptr) {
+             const ffmp::HostExportArgs *host_export = nullptr, const uint8_t *act_bytes = nullptr) {
     const uint64_t m = static_cast<uint64_t>(h->batch);
     const int l = static_cast<int>((h->step_index / m) % static_cast<uint64_t>(h->nlist));
     const bool first = h->step_index % m == 0, last = h->step_index % m == m - 1;
@@ -294,7 +297,7 @@ int run_tick(ffmp_handle *h, int mode, const int64_t *actions, const uint8_t *ma
     if (tev) CK(cudaEventRecord(tev[0], st));
     // the step kernel is always launched as a programmatic dependent of whatever precedes it on the stream (it touches no
     // global memory before its griddepcontrol.wait): behind another step kernel its CTAs are resident when that one drains
-    CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st, nullptr, h->fused, h->tick_pdl));
+    CK(ffmp::launch_step(a, h->use_tma ? &h->tmap : nullptr, st, nullptr, h->fused, h->tick_pdl, act_bytes));
     if (h->io_stats) h->t_tick = now_us();
     if (host_export) {
         // directly behind the step kernel (nothing in between), so that the programmatic dependency pairs the two
@@ -326,7 +329,7 @@ void drop_graphs(ffmp_handle *h) {
 
 // Flush an unfinished group and order `st` after every queued regeneration; later work on `st` needs no further waits.
 int join_and_clear(ffmp_handle *h, cudaStream_t st) {
-    if (h->group_open) if (int rc = launch_regen(h, st, nullptr)) return rc;
+    if (h->group_open) if (int rc = launch_regen(h, st, nullptr, true)) return rc;
     for (int l = 0; l < h->nlist; ++l)
         if (h->regen_pending[l]) { CK(cudaStreamWaitEvent(st, h->ev_regen[l], 0)); h->regen_pending[l] = false; }
     return FFMP_OK;
@@ -367,6 +370,7 @@ int ffmp_create(const ffmp_cfg *cfg, ffmp_handle **out) {
     if (const char *f = std::getenv("FFMP_STEP_FUSED")) h->fused = std::atoi(f) != 0;
     if (const char *f = std::getenv("FFMP_HOST_IO")) h->host_io = std::atoi(f);
     if (const char *f = std::getenv("FFMP_TICK_PDL")) h->tick_pdl = std::atoi(f) != 0;
+    if (const char *f = std::getenv("FFMP_ACT_PARAM")) h->act_param = std::atoi(f) != 0;
     if (const char *f = std::getenv("FFMP_REGEN_WAIT")) h->always_wait = std::atoi(f) != 0;
     if (const char *f = std::getenv("FFMP_HOST_IO_STATS")) h->io_stats = std::atoi(f) != 0;
     h->ws = workspace_layout(cfg);
@@ -646,7 +650,18 @@ int ffmp_step_host_async(ffmp_handle *h, const int64_t *actions_host, float *rew
     const int64_t *actions_dev = nullptr;
     if (out_alias && h->host_io >= 2) actions_dev = static_cast<const int64_t *>(mapped_alias(actions_host));
     if (h->io_stats) h->t_alias = now_us();
-    if (!actions_dev) {
+    const uint8_t *act_bytes = nullptr;
+    if (!actions_dev && h->act_param && h->use_tma && h->fused && !h->trace && N <= static_cast<size_t>(ffmp::ACT_PARAM_MAX)) {
+        // up to ACT_PARAM_MAX envs: the actions ride in the step kernel's launch as one byte per env (255 = out of range, which
+        // the kernel reports exactly like an out-of-range int64); no copy engine sits between the caller's buffer and the kernel
+        uint8_t *p = h->act_bytes;
+        for (size_t i = 0; i < N; ++i) {
+            const uint64_t v = static_cast<uint64_t>(actions_host[i]);
+            p[i] = v < 28 ? static_cast<uint8_t>(v) : static_cast<uint8_t>(255);
+        }
+        act_bytes = p;
+    }
+    if (!actions_dev && !act_bytes) {
         CK(cudaMemcpyAsync(h->actions(), actions_host, N * sizeof(int64_t), cudaMemcpyHostToDevice, st));
         actions_dev = h->actions();
     }
@@ -659,13 +674,13 @@ int ffmp_step_host_async(ffmp_handle *h, const int64_t *actions_host, float *rew
         ea.flag = h->flag_dev;
         ea.value = ++h->flag_seq;
         if (h->io_stats) ea.stamps = reinterpret_cast<unsigned long long *>(h->flag_dev + 2);
-        if (int rc = run_tick(h, 0, actions_dev, nullptr, st, &ea)) return rc;
+        if (int rc = run_tick(h, 0, actions_dev, nullptr, st, &ea, act_bytes)) return rc;
         h->wait_mode = 1;
         h->wait_stream = st;
         if (h->io_stats) h->t_queued = now_us();
         return FFMP_OK;
     }
-    if (int rc = run_tick(h, 0, actions_dev, nullptr, st)) return rc;
+    if (int rc = run_tick(h, 0, actions_dev, nullptr, st, nullptr, act_bytes)) return rc;
     if (packed) {
         CK(cudaMemcpyAsync(h0, d0, 22 * N, cudaMemcpyDeviceToHost, st));
     } else {
@@ -1044,7 +1059,7 @@ int ffmp_join(ffmp_handle *h, void *stream) {
     if (!h) return fail(FFMP_ERR_ARG, "handle is null");
     DeviceGuard guard(h->cfg.device);
     // episode ends of an unfinished group of ticks (regen_batch > 1) are handed to the regeneration now
-    if (h->group_open) if (int rc = launch_regen(h, static_cast<cudaStream_t>(stream), nullptr)) return rc;
+    if (h->group_open) if (int rc = launch_regen(h, static_cast<cudaStream_t>(stream), nullptr, true)) return rc;
     for (int l = 0; l < h->nlist; ++l)
         if (h->regen_pending[l]) CK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), h->ev_regen[l], 0));
     return FFMP_OK;

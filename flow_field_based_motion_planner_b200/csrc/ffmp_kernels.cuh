@@ -46,6 +46,8 @@ struct FlowArgs {
     uint32_t neg1, one;         // 0xFFFFFFFF and 1 (set by the launcher): opaque IMAD multipliers, see flow_field.cu
     uint32_t *host_done;        // optional word in mapped host memory: the last CTA publishes host_done_value there, so the host
     uint32_t host_done_value;   //   can tell without a CUDA call that this (background regeneration) launch has completed
+    int latency;                // 1: the caller waits for this launch (a join's flush, a reset of a few envs): 96 < G <= 128 uses the
+                                //    four-warps-per-grid kernel
 };
 
 struct StepArgs {
@@ -140,8 +142,11 @@ cudaError_t launch_scenarios(const ScenarioArgs &a, int grid, cudaStream_t st);
 cudaError_t launch_flow_field(const FlowArgs &a, int grid, cudaStream_t st);
 // tmap: TMA descriptor of the flow planes [S*N][G][G] (box W x ceil16(W)) or null -> plain-load observe kernel
 // fused: run the scalar step inside the TMA observe kernel (one launch per tick); ignored without a tensor map
+// act_bytes: host pointer to N <= ACT_PARAM_MAX action bytes (255 = invalid) that travel inside the launch as a by-value kernel
+//            parameter (fused TMA kernel only; the caller checks launch_step_takes_action_bytes), or null (a.actions on the device)
+constexpr int ACT_PARAM_MAX = 4096;
 cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t st, cudaEvent_t between = nullptr,
-                        bool fused = true, bool pdl = false);
+                        bool fused = true, bool pdl = false, const uint8_t *act_bytes = nullptr);
 cudaError_t launch_rewarder(const RewarderArgs &a, cudaStream_t st);
 cudaError_t launch_terminal_obs(const StepArgs &a, cudaStream_t st);      // step.cu: behind a mode-0 step when term_frames is set
 int flow_field_max_grid(int G);            // resident CTAs for a full wave (multiple of the SM count)

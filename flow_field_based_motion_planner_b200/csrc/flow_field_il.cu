@@ -20,6 +20,7 @@
 //     pattern instead of a per-cell select); flow bytes come from a 16 x 16 x 2 transpose of 4-bit selector planes and ONE
 //     PRMT table look-up per four cells.
 // Algorithmic HBM bytes: 6 B/cell (1 occupancy read + 4 cost write + 1 flow write).
+#include <cstdlib>
 #include <type_traits>
 
 #include "flow_bits.cuh"
@@ -40,6 +41,132 @@ __device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) 
     uint32_t r;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
     return r;
+}
+
+__device__ __forceinline__ int pidx(int k, int r, int ln) { return ((k * 4 + r) * 32 + ln) * 4; }
+__device__ __forceinline__ void ld4(const uint32_t *p, uint32_t (&v)[4]) {
+    const uint4 t = *reinterpret_cast<const uint4 *>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void st4(uint32_t *p, const uint32_t (&v)[4]) { *reinterpret_cast<uint4 *>(p) = make_uint4(v[0], v[1], v[2], v[3]); }
+
+// One pass of the output phase: row R = 4 * lane + r of the grid for every lane of the calling warp (32 rows at a time).  Flow
+// direction -> flow bytes; cost planes -> int32.  Both outputs go through the warp's swizzled staging buffer so that a warp
+// store instruction writes whole 128-byte lines (a lane that stores its own row 16 bytes at a time costs the LSU 32 wavefronts
+// per instruction).  `pl` = the binary cost planes / reached / free planes in shared memory, `hi` = the L2 scratch planes.
+__device__ __forceinline__ void il_emit_rows(uint32_t *pl, const uint32_t *hi, uint32_t *stage, const int r, const int lane,
+                                             const int G, const int gi, const int gj, const int kmax, uint8_t *flow,
+                                             int32_t *cost) {
+    // staging: row i (one per lane) is 8 chunks of 16 bytes; chunk c sits at position c ^ (i & 7), so that both the row-wise
+    // 16-byte writes of 8 consecutive lanes and the reads along a row are free of bank conflicts
+    auto stage_chunk = [&](int i, int c) -> uint32_t * { return &stage[i * 32 + ((c ^ (i & 7)) << 2)]; };
+    const int R = lane * 4 + r;
+    const int lu = r == 0 ? lane - 1 : lane, ru = r == 0 ? 3 : r - 1;          // row R-1
+    const int ldn = r == 3 ? lane + 1 : lane, rd = r == 3 ? 0 : r + 1;         // row R+1
+    const uint32_t par0 = static_cast<uint32_t>(R + gi + gj) & 1u;
+    uint32_t bk6[4] = {0u, 0u, 0u, 0u};
+    if (cost && kmax == 7) ld4(&hi[pidx(0, r, lane)], bk6);                    // cost bit 7 (L2): requested early
+    rowops::RowIn in;
+    ld4(&pl[pidx(0, r, lane)], in.b1c); ld4(&pl[pidx(1, r, lane)], in.b2c);
+    ld4(&pl[pidx(IL_PVIS, r, lane)], in.Vc); ld4(&pl[pidx(IL_PFREE, r, lane)], in.Fc);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        in.b1u[w] = in.b2u[w] = in.Vu[w] = in.Fu[w] = 0u;
+        in.b1d[w] = in.b2d[w] = in.Vd[w] = in.Fd[w] = 0u;
+    }
+    // a free neighbour of a reached cell is reached: the neighbour rows' reached masks stand in for their free masks
+    if (lu >= 0) {
+        ld4(&pl[pidx(0, ru, lu)], in.b1u); ld4(&pl[pidx(1, ru, lu)], in.b2u);
+        ld4(&pl[pidx(IL_PVIS, ru, lu)], in.Vu);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) in.Fu[w] = in.Vu[w];
+    }
+    if (ldn < 32) {
+        ld4(&pl[pidx(0, rd, ldn)], in.b1d); ld4(&pl[pidx(1, rd, ldn)], in.b2d);
+        ld4(&pl[pidx(IL_PVIS, rd, ldn)], in.Vd);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) in.Fd[w] = in.Vd[w];
+    }
+    {
+        uint32_t n[4][4], fw[32];
+        rowops::direction_nibbles(in, par0, n);
+        rowops::flow_row_words(n, fw);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4 *>(stage_chunk(lane, c)) = make_uint4(fw[4 * c], fw[4 * c + 1], fw[4 * c + 2], fw[4 * c + 3]);
+    }
+    __syncwarp();
+    if ((G & 15) == 0) {
+        // 8 lanes per row, 4 rows per instruction: four whole lines
+        const int c = lane & 7;
+#pragma unroll
+        for (int i0 = 0; i0 < 32; i0 += 4) {
+            const int i = i0 + (lane >> 3), Ri = 4 * i + r;
+            const uint4 t = *reinterpret_cast<const uint4 *>(stage_chunk(i, c));
+            if (Ri < G && 16 * c < G) *reinterpret_cast<uint4 *>(flow + static_cast<size_t>(Ri) * G + 16 * c) = t;
+        }
+    } else {
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+            const int Ri = 4 * i + r;
+            const uint32_t t = stage_chunk(i, lane >> 2)[lane & 3];
+            if (Ri < G && 4 * lane < G) *reinterpret_cast<uint32_t *>(flow + static_cast<size_t>(Ri) * G + 4 * lane) = t;
+        }
+    }
+    __syncwarp();
+    if (cost) {
+        if (kmax <= 7) {
+            // depth < 256: one 32 x 32 bit transpose per row; the row's 32 words (4 cells each) are staged, and lane b
+            // widens word b of every row with one PRMT per cell: a store instruction writes 512 contiguous bytes
+            uint32_t x[32];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) x[8 * w] = ~in.Vc[w];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                uint32_t bk[4];
+                if (k < IL_NPS) ld4(&pl[pidx(k, r, lane)], bk);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) x[8 * w + 1 + k] = (k < IL_NPS ? bk[w] : bk6[w]) | ~in.Vc[w];
+            }
+            rowops::transpose32(x);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<uint4 *>(stage_chunk(lane, c)) = make_uint4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+            __syncwarp();
+            const uint32_t parw = ((static_cast<uint32_t>(r + gi + gj)) & 1u) ? 0x00010001u : 0x01000100u;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+                const int Ri = 4 * i + r;
+                const uint32_t T = stage_chunk(i, lane >> 2)[lane & 3];
+                const rowops::Int4 c4 = rowops::widen_cost4(T, parw);
+                if (Ri < G && 4 * lane < G)
+                    *reinterpret_cast<int4 *>(cost + static_cast<size_t>(Ri) * G + 4 * lane) = make_int4(c4.x, c4.y, c4.z, c4.w);
+            }
+            __syncwarp();
+        } else if (R < G) {
+            // deep maps (>= 256 levels: mazes): cell by cell from the planes
+            int32_t *dst = cost + static_cast<size_t>(R) * G;
+#pragma unroll 1
+            for (int b = 0; 4 * b < G; ++b) {
+                uint32_t v[4];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) v[w] = (par0 ^ static_cast<uint32_t>(w)) & 1u;
+#pragma unroll 1
+                for (int k = 0; k < kmax; ++k) {
+                    uint32_t t[4];
+                    ld4(k < IL_NPS ? &pl[pidx(k, r, lane)] : &hi[pidx(k - IL_NPS, r, lane)], t);
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) v[w] |= ((t[w] >> b) & 1u) << (k + 1);
+                }
+                int4 c;
+                c.x = (in.Vc[0] >> b) & 1u ? static_cast<int>(v[0]) : COST_INF;
+                c.y = (in.Vc[1] >> b) & 1u ? static_cast<int>(v[1]) : COST_INF;
+                c.z = (in.Vc[2] >> b) & 1u ? static_cast<int>(v[2]) : COST_INF;
+                c.w = (in.Vc[3] >> b) & 1u ? static_cast<int>(v[3]) : COST_INF;
+                *reinterpret_cast<int4 *>(dst + 4 * b) = c;
+            }
+        }
+    }
 }
 
 // GEN = true : the scenario (SPEC.md §3) is generated in-kernel from the hash RNG straight into the bit mask (batched env:
@@ -68,16 +195,6 @@ __global__ void __launch_bounds__(32, IL_WARPS_PER_SM) flow_field_il_kernel(Flow
         }
         __syncwarp();
     }
-
-    auto pidx = [&](int k, int r, int ln) { return ((k * 4 + r) * 32 + ln) * 4; };
-    auto ld4 = [&](const uint32_t *p, uint32_t (&v)[4]) {
-        const uint4 t = *reinterpret_cast<const uint4 *>(p);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    };
-    auto st4 = [&](uint32_t *p, const uint32_t (&v)[4]) { *reinterpret_cast<uint4 *>(p) = make_uint4(v[0], v[1], v[2], v[3]); };
-    // staging: row i (one per lane) is 8 chunks of 16 bytes; chunk c sits at position c ^ (i & 7), so that both the row-wise
-    // 16-byte writes of 8 consecutive lanes and the reads along a row are free of bank conflicts
-    auto stage_chunk = [&](int i, int c) -> uint32_t * { return &stage[i * 32 + ((c ^ (i & 7)) << 2)]; };
 
     for (int item = blockIdx.x;; item += gridDim.x) {
         if (a.work) {
@@ -368,113 +485,7 @@ __global__ void __launch_bounds__(32, IL_WARPS_PER_SM) flow_field_il_kernel(Flow
         int32_t *cost = a.cost ? a.cost + plane * cells : nullptr;
 #pragma unroll 1
         for (int r = 0; r < 4; ++r) {
-            const int R = lane * 4 + r;
-            const int lu = r == 0 ? lane - 1 : lane, ru = r == 0 ? 3 : r - 1;          // row R-1
-            const int ldn = r == 3 ? lane + 1 : lane, rd = r == 3 ? 0 : r + 1;         // row R+1
-            const uint32_t par0 = static_cast<uint32_t>(R + gi + gj) & 1u;
-            uint32_t bk6[4] = {0u, 0u, 0u, 0u};
-            if (cost && kmax == 7) ld4(&hi[pidx(0, r, lane)], bk6);                    // cost bit 7 (L2): requested early
-            rowops::RowIn in;
-            ld4(&pl[pidx(0, r, lane)], in.b1c); ld4(&pl[pidx(1, r, lane)], in.b2c);
-            ld4(&pl[pidx(IL_PVIS, r, lane)], in.Vc); ld4(&pl[pidx(IL_PFREE, r, lane)], in.Fc);
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                in.b1u[w] = in.b2u[w] = in.Vu[w] = in.Fu[w] = 0u;
-                in.b1d[w] = in.b2d[w] = in.Vd[w] = in.Fd[w] = 0u;
-            }
-            // a free neighbour of a reached cell is reached: the neighbour rows' reached masks stand in for their free masks
-            if (lu >= 0) {
-                ld4(&pl[pidx(0, ru, lu)], in.b1u); ld4(&pl[pidx(1, ru, lu)], in.b2u);
-                ld4(&pl[pidx(IL_PVIS, ru, lu)], in.Vu);
-#pragma unroll
-                for (int w = 0; w < 4; ++w) in.Fu[w] = in.Vu[w];
-            }
-            if (ldn < 32) {
-                ld4(&pl[pidx(0, rd, ldn)], in.b1d); ld4(&pl[pidx(1, rd, ldn)], in.b2d);
-                ld4(&pl[pidx(IL_PVIS, rd, ldn)], in.Vd);
-#pragma unroll
-                for (int w = 0; w < 4; ++w) in.Fd[w] = in.Vd[w];
-            }
-            {
-                uint32_t n[4][4], fw[32];
-                rowops::direction_nibbles(in, par0, n);
-                rowops::flow_row_words(n, fw);
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    *reinterpret_cast<uint4 *>(stage_chunk(lane, c)) = make_uint4(fw[4 * c], fw[4 * c + 1], fw[4 * c + 2], fw[4 * c + 3]);
-            }
-            __syncwarp();
-            if ((G & 15) == 0) {
-                // 8 lanes per row, 4 rows per instruction: four whole lines
-                const int c = lane & 7;
-#pragma unroll
-                for (int i0 = 0; i0 < 32; i0 += 4) {
-                    const int i = i0 + (lane >> 3), Ri = 4 * i + r;
-                    const uint4 t = *reinterpret_cast<const uint4 *>(stage_chunk(i, c));
-                    if (Ri < G && 16 * c < G) *reinterpret_cast<uint4 *>(flow + static_cast<size_t>(Ri) * G + 16 * c) = t;
-                }
-            } else {
-#pragma unroll 4
-                for (int i = 0; i < 32; ++i) {
-                    const int Ri = 4 * i + r;
-                    const uint32_t t = stage_chunk(i, lane >> 2)[lane & 3];
-                    if (Ri < G && 4 * lane < G) *reinterpret_cast<uint32_t *>(flow + static_cast<size_t>(Ri) * G + 4 * lane) = t;
-                }
-            }
-            __syncwarp();
-            if (cost) {
-                if (kmax <= 7) {
-                    // depth < 256: one 32 x 32 bit transpose per row; the row's 32 words (4 cells each) are staged, and lane b
-                    // widens word b of every row with one PRMT per cell: a store instruction writes 512 contiguous bytes
-                    uint32_t x[32];
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) x[8 * w] = ~in.Vc[w];
-#pragma unroll
-                    for (int k = 0; k < 7; ++k) {
-                        uint32_t bk[4];
-                        if (k < IL_NPS) ld4(&pl[pidx(k, r, lane)], bk);
-#pragma unroll
-                        for (int w = 0; w < 4; ++w) x[8 * w + 1 + k] = (k < IL_NPS ? bk[w] : bk6[w]) | ~in.Vc[w];
-                    }
-                    rowops::transpose32(x);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        *reinterpret_cast<uint4 *>(stage_chunk(lane, c)) = make_uint4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
-                    __syncwarp();
-                    const uint32_t parw = ((static_cast<uint32_t>(r + gi + gj)) & 1u) ? 0x00010001u : 0x01000100u;
-#pragma unroll 8
-                    for (int i = 0; i < 32; ++i) {
-                        const int Ri = 4 * i + r;
-                        const uint32_t T = stage_chunk(i, lane >> 2)[lane & 3];
-                        const rowops::Int4 c4 = rowops::widen_cost4(T, parw);
-                        if (Ri < G && 4 * lane < G)
-                            *reinterpret_cast<int4 *>(cost + static_cast<size_t>(Ri) * G + 4 * lane) = make_int4(c4.x, c4.y, c4.z, c4.w);
-                    }
-                    __syncwarp();
-                } else if (R < G) {
-                    // deep maps (>= 256 levels: mazes): cell by cell from the planes
-                    int32_t *dst = cost + static_cast<size_t>(R) * G;
-#pragma unroll 1
-                    for (int b = 0; 4 * b < G; ++b) {
-                        uint32_t v[4];
-#pragma unroll
-                        for (int w = 0; w < 4; ++w) v[w] = (par0 ^ static_cast<uint32_t>(w)) & 1u;
-#pragma unroll 1
-                        for (int k = 0; k < kmax; ++k) {
-                            uint32_t t[4];
-                            ld4(k < IL_NPS ? &pl[pidx(k, r, lane)] : &hi[pidx(k - IL_NPS, r, lane)], t);
-#pragma unroll
-                            for (int w = 0; w < 4; ++w) v[w] |= ((t[w] >> b) & 1u) << (k + 1);
-                        }
-                        int4 c;
-                        c.x = (in.Vc[0] >> b) & 1u ? static_cast<int>(v[0]) : COST_INF;
-                        c.y = (in.Vc[1] >> b) & 1u ? static_cast<int>(v[1]) : COST_INF;
-                        c.z = (in.Vc[2] >> b) & 1u ? static_cast<int>(v[2]) : COST_INF;
-                        c.w = (in.Vc[3] >> b) & 1u ? static_cast<int>(v[3]) : COST_INF;
-                        *reinterpret_cast<int4 *>(dst + 4 * b) = c;
-                    }
-                }
-            }
+            il_emit_rows(pl, hi, stage, r, lane, G, gi, gj, kmax, flow, cost);
         }
         __syncwarp();
     }
@@ -496,6 +507,182 @@ __global__ void __launch_bounds__(32, IL_WARPS_PER_SM) flow_field_il_kernel(Flow
     }
 }
 
+
+// ---- latency-oriented variant: FOUR warps per grid (background regeneration, small resets) ---------------------------------
+// The warp-per-grid kernel above is the throughput form: no barrier, 16 + 16 mask registers per lane, but one grid takes
+// ~190 levels x 72 instructions on ONE warp — 35-70 us when the SM is shared with step kernels — and the last regeneration of
+// a rollout (or the reset of a single env, the reference's own use) waits for exactly that.  Here thread (warp r, lane l) owns
+// row 4l + r only (4 + 4 mask registers): a level is 8 LOP3 per thread; the rows above / below belong to other warps and are
+// exchanged through a double-buffered 2 KB shared-memory array (slot 32r + l: conflict-free 16-byte accesses), ordered by one
+// block barrier per level; convergence is voted every fourth level by the barrier itself.  The row <-> thread mapping is the
+// one the output phase wants (pass r = rows 4l + r): each warp emits its own pass through its own staging buffer, so the
+// scenario rows, the Gray -> binary conversion and the output run four-wide as well.  Scenario generation only (GEN): rows 0
+// and G-1.. of a generated map are walls, so what the first / last row reads past the grid never matters.
+// Same Gray planes, same row arithmetic and same bytes out as the warp kernel (tests compare both against the oracle).
+constexpr int QUAD_CTAS_PER_SM = 3;
+
+__global__ void __launch_bounds__(128, 4) flow_field_quad_kernel(FlowArgs a) {
+    __shared__ __align__(128) uint32_t pl[IL_NPLX * IL_PW];          // 16 KB: Gray planes 0..5, reached, free
+    __shared__ __align__(128) uint32_t stage[4][IL_STAGE_WORDS];     // 16 KB: one output staging buffer per warp
+    __shared__ __align__(16) uint32_t xch[2][128 * 4];               // 4 KB: the frontier rows of the current / next level
+    __shared__ int s_item;
+
+    const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int G = a.G;
+    const int count = a.count_ptr ? static_cast<int>(*a.count_ptr) : a.count;
+    uint32_t *hi = a.hi_scratch + static_cast<size_t>(blockIdx.x) * (IL_NPG * IL_PW);
+    const uint32_t neg1 = a.neg1, one = a.one, two = a.one + a.one;
+    const int slot = (r * 32 + lane) * 4;
+    const int up_slot = (r > 0 ? (r - 1) * 32 + lane : 96 + lane - 1) * 4;      // row 4l + r - 1 (lane 0 of warp 0: any row)
+    const int dn_slot = (r < 3 ? (r + 1) * 32 + lane : lane + 1) * 4;           // row 4l + r + 1 (lane 31 of warp 3: any row)
+
+    for (int item = blockIdx.x;; item += gridDim.x) {
+        __syncthreads();            // the previous grid's planes have been read by every warp
+        if (a.work) {
+            if (threadIdx.x == 0) s_item = static_cast<int>(atomicAdd(a.work, 1u));
+            __syncthreads();
+            item = s_item;
+        }
+        if (item >= count) break;
+        const uint32_t env = a.env_idx ? a.env_idx[item] : static_cast<uint32_t>(item);
+        const size_t cells = static_cast<size_t>(G) * G;
+        const uint32_t episode = a.episode ? a.episode[item] : a.episode_const;
+        const size_t plane = static_cast<size_t>(episode % a.S) * a.N + env;
+        const uint32_t key = scenario_key(a.seed, a.env_id_base + env, episode);
+        ScenarioParams sp;
+        sp.si = sp.sj = sp.gi = sp.gj = 0; sp.yaw = 0.0f;
+        if (lane == 0) {            // every warp samples the scenario for itself (no block barrier); warp 0 stores the record
+            sp = sample_scenario(key, G, a.goal_mode);
+            if (r == 0) store_scenario_record(a.scen_out + plane * SC_WORDS, sp, key);
+        }
+        sp.si = __shfl_sync(FULL, sp.si, 0); sp.sj = __shfl_sync(FULL, sp.sj, 0);
+        sp.gi = __shfl_sync(FULL, sp.gi, 0); sp.gj = __shfl_sync(FULL, sp.gj, 0);
+        const int gi = sp.gi, gj = sp.gj;
+
+        uint32_t A[4], F[4], P0[4];
+        scenario_free_row_il(key, lane * 4 + r, G, a.block_shift, a.p_thresh, sp, A);
+        st4(&pl[pidx(IL_PFREE, r, lane)], A);
+        {
+            const uint32_t z[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int k = 1; k < IL_NPS; ++k) st4(&pl[pidx(k, r, lane)], z);
+        }
+        {
+            const bool ok = gi >= 0 && gj >= 0 && gi < G && gj < G && lane == (gi >> 2) && r == (gi & 3);
+            const int gw = gj & 3;
+            const uint32_t bit = ok ? (1u << (gj >> 2)) : 0u;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const uint32_t m = w == gw ? (bit & A[w]) : 0u;
+                F[w] = m;
+                A[w] ^= m;
+                P0[w] = 0u;
+            }
+        }
+        st4(&xch[0][slot], F);
+        __syncthreads();
+
+        // ---- the wavefront: one level per barrier ----
+        int buf = 0;
+        auto step = [&]() {
+            uint32_t u[4], d[4], N[4];
+            ld4(&xch[buf][up_slot], u);
+            ld4(&xch[buf][dn_slot], d);
+            const uint32_t lo0 = mask_on_fma(F[3], two), hi3 = F[0] >> 1;
+            N[0] = (lo0 | F[1] | u[0] | d[0]) & A[0];
+            N[1] = (F[0] | F[2] | u[1] | d[1]) & A[1];
+            N[2] = (F[1] | F[3] | u[2] | d[2]) & A[2];
+            N[3] = (F[2] | hi3 | u[3] | d[3]) & A[3];
+            buf ^= 1;
+            st4(&xch[buf][slot], N);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { A[w] = sub_on_fma(A[w], N[w], neg1); F[w] = N[w]; }
+        };
+        uint32_t L = 1;
+        uint32_t s0 = one;
+        for (;; L += 4) {
+            // the plane schedule of the warp kernel: level L+1 toggles plane 0 (registers), level L+3 plane ctz(M), M = (L+3) >> 1
+            const uint32_t M = (L + 3) >> 1;
+            const int k = __ffs(M) - 1;
+            const uint32_t sk = ((M >> (k + 1)) & 1u) ? neg1 : one;
+            const bool resident = k < IL_NPS;
+            uint32_t *pp = resident ? &pl[pidx(k, r, lane)] : &hi[pidx(k - IL_NPS, r, lane)];
+            const bool first = M == (1u << k);                   // the scratch is not zeroed: its first toggle stores
+            step();
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < 4; ++w) P0[w] = mad_u32(A[w], s0, P0[w]);
+            s0 = 0u - s0;
+            step();
+            __syncthreads();
+            uint32_t v[4] = {0u, 0u, 0u, 0u};
+            if (resident || !first) ld4(pp, v);
+            step();
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < 4; ++w) v[w] = mad_u32(A[w], sk, v[w]);
+            st4(pp, v);
+            step();
+            if (!__syncthreads_or((F[0] | F[1] | F[2] | F[3]) != 0u)) break;
+        }
+        const uint32_t Mmax = (L + 2) >> 1;
+        const int kmax = 32 - __clz(Mmax);
+        {
+            uint32_t v[4], f[4];
+            ld4(&pl[pidx(IL_PFREE, r, lane)], f);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) v[w] = f[w] & ~A[w];
+            st4(&pl[pidx(IL_PVIS, r, lane)], v);
+        }
+        // ---- Gray -> binary of the thread's row, in place ----
+        {
+            uint32_t acc[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 1
+            for (int k = kmax - 1; k >= IL_NPS; --k) {
+                uint32_t v[4];
+                uint32_t *p = &hi[pidx(k - IL_NPS, r, lane)];
+                ld4(p, v);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) acc[w] ^= v[w];
+                st4(p, acc);
+            }
+#pragma unroll
+            for (int k = IL_NPS - 1; k >= 1; --k) {
+                uint32_t v[4];
+                uint32_t *p = &pl[pidx(k, r, lane)];
+                ld4(p, v);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) acc[w] ^= v[w];
+                st4(p, acc);
+            }
+#pragma unroll
+            for (int w = 0; w < 4; ++w) acc[w] ^= P0[w];
+            st4(&pl[pidx(0, r, lane)], acc);
+        }
+        __syncthreads();            // the output phase reads the rows above / below, which other warps converted
+        il_emit_rows(pl, hi, stage[r], r, lane, G, gi, gj, kmax, a.flow + plane * cells, a.cost ? a.cost + plane * cells : nullptr);
+    }
+
+    // the last CTA to finish re-arms the regeneration list for its next use
+    if (a.ticket) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t t = atomicAdd(a.ticket, 1u);
+            if (t == gridDim.x - 1) {
+                *a.ticket = 0;
+                if (a.work) *a.work = 0;
+                if (a.count_reset) *a.count_reset = 0;
+                __threadfence();
+                if (a.host_done) {
+                    __threadfence_system();
+                    *reinterpret_cast<volatile uint32_t *>(a.host_done) = a.host_done_value;
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
 
 size_t flow_field_il_scratch_words() { return static_cast<size_t>(IL_NPG) * IL_PW; }
@@ -504,7 +691,24 @@ size_t flow_field_il_scratch_words() { return static_cast<size_t>(IL_NPG) * IL_P
 // 0.155 ms against 0.160 ms at 10 and 0.173 ms at 6) — shorter per-grid latency, hence a shorter tail of the launch.
 int flow_field_il_ctas_per_sm() { return 8; }
 
+// The four-warps-per-grid kernel serves the launches whose LATENCY is what the caller waits for: the flush of an unfinished
+// regeneration group at a join (FlowArgs.latency) and resets of a few envs.  The regeneration launches that run BESIDE step
+// kernels stay on the warp kernel: there the quad kernel's footprint (16 K registers per grid against 5.4 K) costs the step
+// more than its shorter latency returns (profiles/r02e_quad_ab.txt: steady step 21.4 -> 23.4 us with every list on it).
+// FFMP_FLOW_QUAD=0 keeps every launch on the warp kernel (the parity suite runs both); =k (1..4) sets the CTAs per SM.
+static int quad_ctas_per_sm() {
+    const char *e = std::getenv("FFMP_FLOW_QUAD");      // read per launch: the tests switch it between environments
+    if (!e) return QUAD_CTAS_PER_SM;
+    const int v = std::atoi(e);
+    return v < 0 ? 0 : (v > 4 ? 4 : v);
+}
+
 cudaError_t launch_flow_field_il(const FlowArgs &a, int grid, cudaStream_t st) {
+    const int qmax = 148 * quad_ctas_per_sm();
+    if (a.generate && qmax > 0 && (a.latency || (!a.count_ptr && a.count <= qmax))) {
+        flow_field_quad_kernel<<<grid < qmax ? grid : qmax, 128, 0, st>>>(a);
+        return cudaGetLastError();
+    }
     if (a.generate) flow_field_il_kernel<true><<<grid, 32, 0, st>>>(a);
     else flow_field_il_kernel<false><<<grid, 32, 0, st>>>(a);
     return cudaGetLastError();

@@ -10,6 +10,7 @@
 //   rows of loads in flight per thread).  HBM-bound: W^2 read + W^2 written per env-step (+ one more
 //   frame on ring wrap / reset).  Launched with programmatic dependent launch so that its CTAs are
 //   resident and waiting (griddepcontrol.wait) when dynamics_kernel retires.
+#include <cstring>
 #include <mutex>
 #include "ffmp_kernels.cuh"
 
@@ -487,8 +488,14 @@ __device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) 
 
 // WT != 0: the window side is a compile-time constant (the reference's 100): row pitches and unrolled store offsets become
 // immediates, which takes ~40 % of the instructions out of the drain loop.  WT = 0: generic window (a.W).
-template <bool TRACE, int WT>
-__global__ void __launch_bounds__(128) tick_tma_kernel(const __grid_constant__ CUtensorMap tmap, StepArgs a) {
+// PA: the actions travel IN the launch, as a by-value kernel parameter of ACT_PARAM_MAX bytes (one byte per env, 255 = invalid),
+// and are read from the constant bank: a host-buffer step (ffmp_step_host) then needs neither a copy engine in front of the
+// kernel nor a PCIe read inside every CTA's dependent chain.
+template <bool PA> struct ActionBlock { uint8_t a[PA ? ACT_PARAM_MAX : 4]; };
+
+template <bool TRACE, int WT, bool PA = false>
+__global__ void __launch_bounds__(128) tick_tma_kernel(const __grid_constant__ CUtensorMap tmap, StepArgs a,
+                                                       const __grid_constant__ ActionBlock<PA> ab) {
     extern __shared__ __align__(128) uint8_t tile[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ TickShared sh;
@@ -544,7 +551,7 @@ __global__ void __launch_bounds__(128) tick_tma_kernel(const __grid_constant__ C
         int parity = 0;
 
         if (a.mode == 0) {
-            long long act = a.actions[e];
+            long long act = PA ? static_cast<long long>(ab.a[e]) : a.actions[e];
             if (act < 0 || act >= 28) {
                 act = 3;
                 if (lane == 0) atomicOr(a.error_word, 1u);
@@ -772,6 +779,8 @@ static cudaError_t opt_in_shared(size_t smem) {
     if (dev >= 0 && dev < 64 && smem <= configured[dev]) return cudaSuccess;
     ce = cudaFuncSetAttribute(tick_tma_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (ce == cudaSuccess)
+        ce = cudaFuncSetAttribute(tick_tma_kernel<false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (ce == cudaSuccess)
         ce = cudaFuncSetAttribute(tick_tma_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (ce == cudaSuccess)
         ce = cudaFuncSetAttribute(observe_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -779,7 +788,8 @@ static cudaError_t opt_in_shared(size_t smem) {
     return ce;
 }
 
-cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t st, cudaEvent_t between, bool fused, bool pdl) {
+cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t st, cudaEvent_t between, bool fused, bool pdl,
+                        const uint8_t *act_bytes) {
     if (a.N <= 0) return cudaSuccess;
     const size_t smem = tmap ? static_cast<size_t>((a.W + 30) & ~15) * a.W + 16 : 0;
     if (tmap) {
@@ -798,10 +808,19 @@ cudaError_t launch_step(const StepArgs &a, const CUtensorMap *tmap, cudaStream_t
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr;
             cfg.numAttrs = pdl ? 1 : 0;
-            if (a.trace) return cudaLaunchKernelEx(&cfg, tick_tma_kernel<true, 0>, *tmap, a);
-            if (a.W == 100) return cudaLaunchKernelEx(&cfg, tick_tma_kernel<false, 100>, *tmap, a);   // the reference's window
-            if (a.W == 64) return cudaLaunchKernelEx(&cfg, tick_tma_kernel<false, 64>, *tmap, a);     // BASELINE config 2
-            return cudaLaunchKernelEx(&cfg, tick_tma_kernel<false, 0>, *tmap, a);   // the whole tick in one kernel
+            if (act_bytes && !a.trace && a.N <= ACT_PARAM_MAX) {
+                // actions by value (host-buffer steps of up to ACT_PARAM_MAX envs): the bytes are copied into the launch here
+                ActionBlock<true> ab;
+                std::memcpy(ab.a, act_bytes, static_cast<size_t>(a.N));
+                if (a.W == 100) return cudaLaunchKernelEx(&cfg, tick_tma_kernel<false, 100, true>, *tmap, a, ab);
+                if (a.W == 64) return cudaLaunchKernelEx(&cfg, tick_tma_kernel<false, 64, true>, *tmap, a, ab);
+                return cudaLaunchKernelEx(&cfg, tick_tma_kernel<false, 0, true>, *tmap, a, ab);
+            }
+            const ActionBlock<false> none{};
+            if (a.trace) return cudaLaunchKernelEx(&cfg, tick_tma_kernel<true, 0>, *tmap, a, none);
+            if (a.W == 100) return cudaLaunchKernelEx(&cfg, tick_tma_kernel<false, 100>, *tmap, a, none);   // the reference's window
+            if (a.W == 64) return cudaLaunchKernelEx(&cfg, tick_tma_kernel<false, 64>, *tmap, a, none);     // BASELINE config 2
+            return cudaLaunchKernelEx(&cfg, tick_tma_kernel<false, 0>, *tmap, a, none);   // the whole tick in one kernel
         }
     }
     dynamics_kernel<<<(a.N + 127) / 128, 128, 0, st>>>(a);

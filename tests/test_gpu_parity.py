@@ -313,6 +313,17 @@ def test_rollout_with_regeneration_wait_forced(ffmp, monkeypatch):
     rollout_parity(ffmp, 16, 60, seed=28, grid=128, window=100, slots=12, p_occ=0.3, block_shift=0, check_every=30)
 
 
+@pytest.mark.parametrize("grid,bs,p", [(128, 3, 0.1), (128, 0, 0.3), (116, 1, 0.1)])
+def test_rollout_warp_kernel_regeneration(ffmp, monkeypatch, grid, bs, p):
+    """Resets of a few envs and the background regeneration lists run on the four-warps-per-grid kernel
+    (flow_field_quad_kernel); FFMP_FLOW_QUAD=0 keeps them on the warp-per-grid kernel that serves large batches.  Both
+    must produce the oracle's planes (every other 96 < G <= 128 rollout test runs the quad kernel)."""
+    monkeypatch.setenv("FFMP_FLOW_QUAD", "0")
+    rollout_parity(ffmp, 24, 80, seed=31, grid=grid, window=100, p_occ=p, block_shift=bs, max_steps=20, check_every=20)
+    monkeypatch.setenv("FFMP_FLOW_QUAD", "1")
+    rollout_parity(ffmp, 24, 80, seed=31, grid=grid, window=100, p_occ=p, block_shift=bs, max_steps=20, check_every=20)
+
+
 def test_rollout_dense_obstacles_short_episodes(ffmp):
     """p=0.3 per-cell noise: episodes of a few steps, so nearly every step regenerates slots."""
     rollout_parity(ffmp, 32, 200, seed=9, grid=128, window=100, p_occ=0.3, block_shift=0, check_every=50)
@@ -374,12 +385,16 @@ def test_rollout_api_and_host_step(ffmp, cuda_device):
     env.close()
 
 
-@pytest.mark.parametrize("host_io,pinned", [(0, True), (1, True), (2, True), (2, False)])
-def test_host_step_paths(ffmp, cuda_device, monkeypatch, host_io, pinned):
+@pytest.mark.parametrize("host_io,pinned,act_param", [(0, True, 1), (1, True, 1), (2, True, 1), (2, False, 1), (0, True, 0),
+                                                       (1, True, 0), (1, False, 0)])
+def test_host_step_paths(ffmp, cuda_device, monkeypatch, host_io, pinned, act_param):
     """ffmp_step_host through the copy engines (FFMP_HOST_IO=0), with the results written to pinned host memory by the
-    export kernel (1), with the actions read in place as well (2), and with pageable buffers (falls back to copies):
-    200 steps with auto-resets, every host-side result bit-compared with the oracle; step_async / step_wait split."""
+    export kernel (1), with the actions read in place as well (2), and with pageable buffers (falls back to copies); the
+    actions of up to 4096 envs ride in the step kernel's launch as a by-value parameter unless FFMP_ACT_PARAM=0 (then they
+    are copied to the device first).  200 steps with auto-resets, every host-side result bit-compared with the oracle;
+    step_async / step_wait split."""
     monkeypatch.setenv("FFMP_HOST_IO", str(host_io))
+    monkeypatch.setenv("FFMP_ACT_PARAM", str(act_param))
     N = 64
     env = ffmp.FFMPVectorEnv(N, seed=31, grid=64, window=32, max_steps=20)
     orc = oracle.OracleVectorEnv(N, seed=31, grid=64, window=32, max_steps=20)
@@ -430,6 +445,14 @@ def test_invalid_actions_and_errors(ffmp, cuda_device):
     env.reset()
     env.step(torch.tensor([3, 99, -5, 27], device=cuda_device))
     assert env.error_word() & 1
+    # the same through the host-buffer step (actions inside the launch, one byte per env: out of range must stay out of range)
+    env2 = ffmp.FFMPVectorEnv(4, grid=64, window=32)
+    env2.reset()
+    env2.step_host(torch.tensor([3, 0, 27, 5]).pin_memory())
+    assert env2.error_word() == 0
+    env2.step_host(torch.tensor([3, 255 + 28, -(2 ** 40), 2 ** 33 + 1]).pin_memory())
+    assert env2.error_word() & 1
+    env2.close()
     with pytest.raises(ValueError):
         env.step(torch.zeros(5, dtype=torch.int64, device=cuda_device))
     # ffmp_bind rejects output pointers the kernels' float2 / 4-byte stores cannot take
