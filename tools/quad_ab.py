@@ -36,6 +36,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         env.step_host(ha[i])
     e2e = (time.perf_counter() - t0) * 1e6 / 200
     err = env.error_word()
+    torch.cuda.synchronize(); t0 = time.perf_counter(); env.reset(); torch.cuda.synchronize()
+    reset_ms = (time.perf_counter() - t0) * 1e3
     env.close()
     one = ffmp.FFMPVectorEnv(1, grid=128, window=100, seed=5)
     one.reset(); torch.cuda.synchronize()
@@ -46,7 +48,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     print(json.dumps({"quad": os.environ.get("FFMP_FLOW_QUAD", "default"), "S": S, "m": m, "steady_us": round(steady, 2),
                       "short20_us_median": round(short[10], 2), "short20_us_min": round(short[0], 2),
                       "tick_us": round(kt["tick_ms"] * 1e3, 2), "regen_launch_us": round(kt["regen_ms"] * 1e3, 2),
-                      "step_host_us": round(e2e, 2), "reset_1env_us": round(reset1, 1), "err": err}))
+                      "step_host_us": round(e2e, 2), "reset_1env_us": round(reset1, 1), "reset_4096env_ms": round(reset_ms, 2), "err": err}))
 else:
     runs = [({"FFMP_FLOW_QUAD": "0"}, 16, 3), ({}, 16, 3), ({"FFMP_FLOW_QUAD": "4"}, 16, 3), ({"FFMP_FLOW_QUAD": "0"}, 8, 1), ({}, 8, 1)]
     for e, S, m in runs:
