@@ -324,6 +324,14 @@ def test_rollout_warp_kernel_regeneration(ffmp, monkeypatch, grid, bs, p):
     rollout_parity(ffmp, 24, 80, seed=31, grid=grid, window=100, p_occ=p, block_shift=bs, max_steps=20, check_every=20)
 
 
+@pytest.mark.parametrize("dt,ring", [(0.1, 3), (0.3, 3), (0.3, 8), (0.16, 2)])
+def test_rollout_long_steps_and_short_rings(ffmp, dt, ring):
+    """Steps of up to 3.6 cells (dt = 0.3 s at 0.6 m/s) and rings that wrap every step / every other step (the older frame is
+    refetched at the previous pose on a wrap).  Also the regression test of the superset-window experiment."""
+    rollout_parity(ffmp, 32, 120, seed=41, grid=128, window=100, ring=ring, dt=dt, check_every=40)
+    rollout_parity(ffmp, 24, 90, seed=42, grid=64, window=32, ring=ring, dt=dt, max_steps=15, check_every=30)
+
+
 def test_rollout_dense_obstacles_short_episodes(ffmp):
     """p=0.3 per-cell noise: episodes of a few steps, so nearly every step regenerates slots."""
     rollout_parity(ffmp, 32, 200, seed=9, grid=128, window=100, p_occ=0.3, block_shift=0, check_every=50)
