@@ -347,19 +347,22 @@ def run_ours(a):
         # ---- e2e: public Python API with HOST buffers (pinned actions in, reward/done/goal/velocity out) ----
         k2 = max(10, min(a.steps, 2000))
         host_actions = [torch.randint(0, 28, (N,), dtype=torch.int64).pin_memory() for _ in range(16)]
-        # warm-up of the host side as well: the launch path runs ~4 us per step slower on a core that has just left a
-        # blocking wait (tools/e2e_window.py), so a few milliseconds of steps precede the timed ones
-        for i in range(max(20, 300)):
+        # warm-up: in a fresh process the host-buffer step takes ~37 us for its first ~500 calls (~20 ms) and 32.5 us from then
+        # on, whatever ran on the GPU before (profiles/r02f_e2e_settling.txt), so 1000 untimed steps precede the timed ones
+        for i in range(1000):
             env.step_host(host_actions[i % 16])
         barrier()
         t0 = time.perf_counter()
         for i in range(k2):
             env.step_host(host_actions[i % 16])
+        t1 = time.perf_counter()
         env.join()
         torch.cuda.synchronize()
-        dt = max_over_ranks(time.perf_counter() - t0)
+        t2 = time.perf_counter()
+        dt = max_over_ranks(t2 - t0)
         e2e = {"value": world * N * k2 / dt, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step * world,
                "d2h_bytes_per_step": env.d2h_bytes_per_step * world, "steps": k2,
+               "us_per_step_calls_only": (t1 - t0) * 1e6 / k2, "join_and_sync_us": (t2 - t1) * 1e6,
                "note": "FFMPVectorEnv.step_host every step, host buffers in and out: the caller's pinned int64 actions are "
                        "narrowed to one byte per env on the host and ride inside the step kernel's launch as a by-value "
                        "parameter (up to 4096 envs per GPU; a cudaMemcpyAsync above that), reward/done/flags/relative_goal/velocity "
