@@ -159,16 +159,17 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # CPU legs: the oracle port on the host cores (test infrastructure used as the *baseline*, never shipped)
 # ------------------------------------------------------------------------------------------------------
-def cpu_port_throughput(a, envs_per_thread, steps, warmup, threads):
+def cpu_port_throughput(a, envs_per_thread, steps, warmup, threads, repeats=1):
     """env-steps/s of the C oracle (oracle/ffmp_oracle.c) with `threads` host threads, each stepping its own
-    shard of `envs_per_thread` envs of the bench workload (ctypes releases the GIL)."""
+    shard of `envs_per_thread` envs of the bench workload (ctypes releases the GIL).  repeats > 1: the `steps`-step window
+    is timed that many times back to back and the median is returned (a 20-step window of a 16-thread run is ~20 ms)."""
     import numpy as np
     import oracle
     shards = [oracle.OracleVectorEnv(envs_per_thread, grid=a.grid, window=a.window, goal_mode=a.goal_mode,
                                      p_occ=a.p_occ, seed=a.seed, env_id_base=i * envs_per_thread,
                                      block_shift=a.block_shift) for i in range(threads)]
     rng = np.random.default_rng(a.seed)
-    acts = rng.integers(0, 28, (warmup + steps, threads, envs_per_thread))
+    acts = rng.integers(0, 28, (warmup + steps * repeats, threads, envs_per_thread))
     for s in shards:
         s.reset()
 
@@ -185,7 +186,8 @@ def cpu_port_throughput(a, envs_per_thread, steps, warmup, threads):
         return time.perf_counter() - t0
 
     run(0, warmup)
-    dt = run(warmup, warmup + steps)
+    dts = sorted(run(warmup + r * steps, warmup + (r + 1) * steps) for r in range(repeats))
+    dt = dts[len(dts) // 2]
     for s in shards:
         s.close()
     return threads * envs_per_thread * steps / dt, dt
@@ -202,8 +204,10 @@ def run_reference(a):
     envs_per_thread = 32 if a.grid <= 128 else 1
     steps = max(1, min(a.steps, 200 if a.grid <= 128 else 20))
     warmup = max(3, min(a.warmup, 10 if a.grid <= 128 else 3))
-    v, dt = cpu_port_throughput(a, envs_per_thread, steps, warmup, cores)
-    sample = f"{cores} threads x {envs_per_thread} envs x {steps} steps of the same workload (C oracle port, gcc -O2)"
+    repeats = 7 if a.grid <= 128 else 1
+    v, dt = cpu_port_throughput(a, envs_per_thread, steps, warmup, cores, repeats)
+    sample = (f"{cores} threads x {envs_per_thread} envs x {steps} steps of the same workload (C oracle port, gcc -O2)"
+              + (f", median of {repeats} back-to-back windows" if repeats > 1 else ""))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": a.scaling,
             "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic", "config": workload_config(a, a.gpus),
