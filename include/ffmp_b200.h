@@ -136,7 +136,10 @@ int ffmp_rollout_graphed(ffmp_handle *h, const int64_t *actions_dev, int32_t T, 
  *     flags, the five host destinations are adjacent in the same order (one 22*N-byte block each, 16-byte aligned, N even)
  *     and the host block is pinned (cudaHostAlloc / cudaHostRegister).  Then a small kernel queued behind the step writes
  *     the host block directly and publishes a completion word in mapped memory which the call spins on: no device-to-host
- *     copy engine, no stream synchronisation.  The actions (8 N bytes) go in with one cudaMemcpyAsync.
+ *     copy engine, no stream synchronisation.  Up to 4096 envs the actions travel INSIDE the step kernel's launch: the call
+ *     narrows them to one byte per env (255 for anything outside [0, 28), which the kernel flags in the error word like an
+ *     out-of-range int64) and passes the block as a by-value kernel parameter — no copy engine on the way in either
+ *     (FFMP_ACT_PARAM=0: off).  Above 4096 envs they go in with one cudaMemcpyAsync (8 N bytes).
  *   - Otherwise: cudaMemcpyAsync in, step, cudaMemcpyAsync out (one copy when both blocks are packed), stream sync.
  * FFMP_HOST_IO in the environment at ffmp_create selects the path: 0 copy engines both ways, 1 (default) mapped results,
  * 2 mapped results and actions read in place over PCIe by the step kernel (faster on some hosts, slower on others:
