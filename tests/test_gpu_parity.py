@@ -112,6 +112,16 @@ def test_rollout_large_map_config4_shape(ffmp):
     rollout_parity(ffmp, 8, 150, seed=5, grid=256, window=100, check_every=75)
 
 
+def test_two_devices_in_one_process_large_shared_memory(ffmp):
+    """the >48 KB dynamic shared-memory opt-in belongs to the device; one process driving two GPUs through the
+    C-ABI must get it on both (G = 256 rows kernel: 66 KB per CTA; W = 212 step kernel: 51 KB per CTA).  Skipped on one GPU."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        rollout_parity(ffmp, 4, 24, seed=51, grid=256, window=212, device=dev, max_steps=10, check_every=12)
+        rollout_parity(ffmp, 3, 12, seed=52, grid=512, window=100, p_occ=0.3, block_shift=0, slots=3, device=dev, check_every=6)
+
+
 def test_flow_field_without_cost_output(ffmp, cuda_device):
     occs, goals = [], []
     for k in range(8):
