@@ -512,12 +512,24 @@ int ffmp_reset(ffmp_handle *h, const uint8_t *mask_dev, void *stream) {
     const ffmp_cfg &c = h->cfg;
     CK(cudaMemsetAsync(h->b.state, 0, static_cast<size_t>(c.num_envs) * ffmp::ST_WORDS * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(h->b.workspace, 0, h->ws.actions, st));  // error word + regen lists
-    for (int s = 0; s < c.slots; ++s) {
+    if (ffmp::flow_field_takes_all_slots(c.grid)) {
+        // the interleaved-layout kernels take every scenario slot in ONE launch (item -> env, slot): a single env's reset is one
+        // launch of `slots` grids on the four-warps-per-grid kernel instead of `slots` launches of one grid
         ffmp::FlowArgs fa = flow_args(h);
-        fa.count = c.num_envs; fa.episode_const = static_cast<uint32_t>(s);
+        const long long total = static_cast<long long>(c.num_envs) * c.slots;
+        fa.count = static_cast<int>(total); fa.episode_const = 0; fa.all_slots = 1;
         fa.ticket = h->reset_ticket(); fa.work = h->reset_work();
-        CK(ffmp::launch_flow_field(fa, h->ff_grid, st));
+        const int maxg = ffmp::flow_field_max_grid(c.grid);
+        CK(ffmp::launch_flow_field(fa, total < maxg ? static_cast<int>(total) : maxg, st));
         h->launches += 1;
+    } else {
+        for (int s = 0; s < c.slots; ++s) {
+            ffmp::FlowArgs fa = flow_args(h);
+            fa.count = c.num_envs; fa.episode_const = static_cast<uint32_t>(s);
+            fa.ticket = h->reset_ticket(); fa.work = h->reset_work();
+            CK(ffmp::launch_flow_field(fa, h->ff_grid, st));
+            h->launches += 1;
+        }
     }
     h->p = 1;
     h->step_index = 0;

@@ -46,6 +46,8 @@ struct FlowArgs {
     uint32_t neg1, one;         // 0xFFFFFFFF and 1 (set by the launcher): opaque IMAD multipliers, see flow_field.cu
     uint32_t *host_done;        // optional word in mapped host memory: the last CTA publishes host_done_value there, so the host
     uint32_t host_done_value;   //   can tell without a CUDA call that this (background regeneration) launch has completed
+    int all_slots;              // 1 (generate, 96 < G <= 128): the launch covers every scenario slot of N envs — item -> env = item % N,
+                                //    episode = episode_const + item / N, count = N * slots (a full reset in ONE launch)
     int latency;                // 1: the caller waits for this launch (a join's flush, a reset of a few envs): 96 < G <= 128 uses the
                                 //    four-warps-per-grid kernel
 };
@@ -152,5 +154,6 @@ cudaError_t launch_terminal_obs(const StepArgs &a, cudaStream_t st);      // ste
 int flow_field_max_grid(int G);            // resident CTAs for a full wave (multiple of the SM count)
 size_t flow_field_scratch_words(int G);    // hi_scratch words per CTA
 bool flow_field_supported(int G);
+bool flow_field_takes_all_slots(int G);    // FlowArgs.all_slots (a full reset in one launch) is available for this grid size
 
 }  // namespace ffmp

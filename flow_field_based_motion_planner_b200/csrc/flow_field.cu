@@ -621,7 +621,13 @@ int flow_field_max_grid(int G) {
     return 148 * per_sm;
 }
 
+// FlowArgs.all_slots is understood by the interleaved-layout kernels (flow_field_il.cu) only
+bool flow_field_takes_all_slots(int G) {
+    return G > 96 && G <= 128 && !flow_field_wide_supported(G) && !(flow_field_rows_usable(G) && rows_for_small());
+}
+
 cudaError_t launch_flow_field(const FlowArgs &a_in, int grid, cudaStream_t st) {
+    if (a_in.all_slots && !flow_field_takes_all_slots(a_in.G)) return cudaErrorInvalidValue;
     if (grid <= 0) return cudaSuccess;
     if (flow_field_wide_supported(a_in.G)) return launch_flow_field_wide(a_in, grid, st);
     if (a_in.G > 128 || (flow_field_rows_usable(a_in.G) && rows_for_small())) return launch_flow_field_large(a_in, grid, st);

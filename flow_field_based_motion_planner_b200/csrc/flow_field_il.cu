@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(32, IL_WARPS_PER_SM) flow_field_il_kernel(Flow
             item = __shfl_sync(FULL, item, 0);
         }
         if (item >= count) break;
-        const uint32_t env = a.env_idx ? a.env_idx[item] : static_cast<uint32_t>(item);
+        const uint32_t env = a.all_slots ? static_cast<uint32_t>(item % a.N)
+                                         : (a.env_idx ? a.env_idx[item] : static_cast<uint32_t>(item));
         const size_t cells = static_cast<size_t>(G) * G;
         size_t plane;
         int gi, gj;
@@ -210,7 +211,8 @@ __global__ void __launch_bounds__(32, IL_WARPS_PER_SM) flow_field_il_kernel(Flow
 
         if (GEN) {
             // ---- 1g. scenario parameters (lane 0) and the free-cell mask straight from the hash ----
-            const uint32_t episode = a.episode ? a.episode[item] : a.episode_const;
+            const uint32_t episode = a.all_slots ? a.episode_const + static_cast<uint32_t>(item / a.N)
+                                                 : (a.episode ? a.episode[item] : a.episode_const);
             plane = static_cast<size_t>(episode % a.S) * a.N + env;
             const uint32_t key = scenario_key(a.seed, a.env_id_base + env, episode);
             ScenarioParams sp;
@@ -544,9 +546,11 @@ __global__ void __launch_bounds__(128, 4) flow_field_quad_kernel(FlowArgs a) {
             item = s_item;
         }
         if (item >= count) break;
-        const uint32_t env = a.env_idx ? a.env_idx[item] : static_cast<uint32_t>(item);
+        const uint32_t env = a.all_slots ? static_cast<uint32_t>(item % a.N)
+                                         : (a.env_idx ? a.env_idx[item] : static_cast<uint32_t>(item));
         const size_t cells = static_cast<size_t>(G) * G;
-        const uint32_t episode = a.episode ? a.episode[item] : a.episode_const;
+        const uint32_t episode = a.all_slots ? a.episode_const + static_cast<uint32_t>(item / a.N)
+                                             : (a.episode ? a.episode[item] : a.episode_const);
         const size_t plane = static_cast<size_t>(episode % a.S) * a.N + env;
         const uint32_t key = scenario_key(a.seed, a.env_id_base + env, episode);
         ScenarioParams sp;
