@@ -342,6 +342,17 @@ def test_rollout_long_steps_and_short_rings(ffmp, dt, ring):
     rollout_parity(ffmp, 24, 90, seed=42, grid=64, window=32, ring=ring, dt=dt, max_steps=15, check_every=30)
 
 
+@pytest.mark.parametrize("switch", ["FFMP_STEP_FUSED=0", "FFMP_TICK_PDL=0", "FFMP_TRACE=1"])
+def test_rollout_under_library_switches(ffmp, monkeypatch, switch):
+    """Every environment switch that selects another launch path has a parity run: the two-kernel step (dynamics + observe, also
+    what grids without a tensor map use), step kernels without the programmatic-dependent attribute, the tracing variant of the
+    step kernel (FFMP_FLOW_QUAD, FFMP_ACT_PARAM, FFMP_HOST_IO, FFMP_REGEN_WAIT, FFMP_FLOW_ROWS, FFMP_SCAN_GENERIC: tests above)."""
+    k, v = switch.split("=")
+    monkeypatch.setenv(k, v)
+    rollout_parity(ffmp, 24, 60, seed=61, grid=128, window=100, max_steps=20, check_every=30)
+    rollout_parity(ffmp, 16, 40, seed=62, grid=64, window=32, ring=3, slots=3, max_steps=9, check_every=20)
+
+
 def test_rollout_dense_obstacles_short_episodes(ffmp):
     """p=0.3 per-cell noise: episodes of a few steps, so nearly every step regenerates slots."""
     rollout_parity(ffmp, 32, 200, seed=9, grid=128, window=100, p_occ=0.3, block_shift=0, check_every=50)
