@@ -106,6 +106,33 @@ def test_flow_field_large_maps_bit_exact(ffmp, cuda_device, G):
     assert np.array_equal(flow2[0], oracle.flow_field(cases[0][1], *cases[0][2])[2])
 
 
+def test_flow_field_cluster_variant_bit_exact(ffmp, cuda_device, monkeypatch):
+    """FFMP_FLOW_CLUSTER=1: maps of 384 < G <= 512 on a thread-block cluster of two CTAs per grid (rows split at 256, the seam row
+    exchanged through DSMEM, barrier.cluster per level, cluster-wide convergence vote and hand-out) — BASELINE config 4's
+    "multi-CTA wavefront per env".  Same bytes as the one-CTA kernel: special maps (incl. goals on either side of the seam and
+    corridors crossing it), generated maps, and a config-4 rollout with its background regeneration."""
+    monkeypatch.setenv("FFMP_FLOW_CLUSTER", "1")
+    for G in (512, 448):
+        cases = special_cases(G)
+        cost, flow = run_flow(ffmp, cuda_device, [c[1] for c in cases], [c[2] for c in cases])
+        for k, (name, occ, goal) in enumerate(cases):
+            ec, ed, ef = oracle.flow_field(occ, goal[0], goal[1])
+            assert np.array_equal(cost[k], ec), (G, name, "cost", int((cost[k] != ec).sum()))
+            assert np.array_equal(flow[k], ef), (G, name, "flow", int((flow[k] != ef).sum()))
+    occs, goals = [], []
+    for k in range(7):
+        o, _, _, cells = oracle.scenario(9, k, 0, 512, p_occ=0.3, block_shift=0)
+        occs.append(np.array(o, copy=True))
+        goals.append((cells[2], cells[3]) if k % 2 else (250 + 3 * k, 40 + 60 * k))      # goals next to the seam (rows 255 / 256) too
+    for k in range(7):
+        occs[k][goals[k][0], goals[k][1]] = 0
+    cost, flow = run_flow(ffmp, cuda_device, occs, goals)
+    for k in range(7):
+        ec, _, ef = oracle.flow_field(occs[k], goals[k][0], goals[k][1])
+        assert np.array_equal(cost[k], ec) and np.array_equal(flow[k], ef), k
+    rollout_parity(ffmp, 6, 60, seed=4, grid=512, window=100, p_occ=0.30, block_shift=0, slots=3, check_every=30)
+
+
 def test_rollout_large_map_config4_shape(ffmp):
     """config 4 per-env shape: 512x512 grid with dense i.i.d. obstacles (p=0.30), W=100."""
     rollout_parity(ffmp, 6, 120, seed=4, grid=512, window=100, p_occ=0.30, block_shift=0, slots=3, check_every=60)
