@@ -64,6 +64,25 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// End of a flow-field launch, called by ONE thread per CTA after the CTA's last grid (the CTA barrier of the grid loop orders the
+// other threads' stores before it): fence, take a ticket; the LAST CTA re-arms the ticket, the dynamic hand-out counter and the
+// regeneration list's count for their next use and, for background regenerations, publishes the launch's sequence number in
+// mapped host memory (every CTA fenced its writes before it took its ticket, so the launch's results are visible by then).
+__device__ __forceinline__ void flow_launch_epilogue(const FlowArgs &a) {
+    __threadfence();
+    const uint32_t t = atomicAdd(a.ticket, 1u);
+    if (t == gridDim.x - 1) {
+        *a.ticket = 0;
+        if (a.work) *a.work = 0;
+        if (a.count_reset) *a.count_reset = 0;
+        __threadfence();
+        if (a.host_done) {
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t *>(a.host_done) = a.host_done_value;
+        }
+    }
+}
+
 // 8x8 bit-matrix transpose of the 64-bit value hi:lo (Hacker's Delight 7-3), on 32-bit halves
 __device__ __forceinline__ void transpose8(uint32_t &lo, uint32_t &hi) {
     uint32_t t;

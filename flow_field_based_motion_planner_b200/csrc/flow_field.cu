@@ -561,20 +561,7 @@ __global__ void __launch_bounds__(32, 16) flow_field_warp_kernel(FlowArgs a) {
     }
 
     // the last CTA to finish re-arms the regeneration list for its next use
-    if (a.ticket && lane == 0) {
-        __threadfence();
-        const uint32_t t = atomicAdd(a.ticket, 1u);
-        if (t == gridDim.x - 1) {
-            *a.ticket = 0;
-            if (a.work) *a.work = 0;
-            if (a.count_reset) *a.count_reset = 0;
-            __threadfence();
-            if (a.host_done) {       // every CTA fenced its writes before it took its ticket: the launch's results are visible
-                __threadfence_system();
-                *reinterpret_cast<volatile uint32_t *>(a.host_done) = a.host_done_value;
-            }
-        }
-    }
+    if (a.ticket && lane == 0) flow_launch_epilogue(a);
 }
 
 }  // namespace

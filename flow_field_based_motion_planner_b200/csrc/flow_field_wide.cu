@@ -590,20 +590,7 @@ __global__ void __launch_bounds__(WD_T, 2) flow_field_wide_kernel(FlowArgs a) {
     }
 
     // the last CTA to finish re-arms the regeneration list for its next use
-    if (a.ticket && tid == 0) {
-        __threadfence();
-        const uint32_t t = atomicAdd(a.ticket, 1u);
-        if (t == gridDim.x - 1) {
-            *a.ticket = 0;
-            if (a.work) *a.work = 0;
-            if (a.count_reset) *a.count_reset = 0;
-            __threadfence();
-            if (a.host_done) {
-                __threadfence_system();
-                *reinterpret_cast<volatile uint32_t *>(a.host_done) = a.host_done_value;
-            }
-        }
-    }
+    if (a.ticket && tid == 0) flow_launch_epilogue(a);
 }
 
 }  // namespace
